@@ -1,0 +1,225 @@
+/*
+ * octfusion_b200 -- C ABI of the B200 (sm_100a) kernels behind the OctFusion denoising
+ * U-Net hot path.
+ *
+ * The reference (octree-nn/octfusion) has NO native layer on this path: every operator below
+ * is a sequence of ATen library calls issued from Python.  This header is the
+ * boundary a maintainer of the reference would bind (ctypes stub: INTEGRATION.md); each entry
+ * point names the reference function (file:line under the reference tree) whose arithmetic it
+ * replaces.
+ *
+ * Conventions
+ *   - plain device pointers and sizes; no torch / ATen types; caller owns every buffer
+ *     (outputs and workspaces included); nothing is allocated, freed or synchronised inside
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant
+ *     per stream, CUDA-graph capturable
+ *   - return value: 0 = launched; negative = rejected before any launch (OF_E_*); the
+ *     text of the last error of the calling thread is available from of_last_error()
+ *   - dtype: OF_F32 (0) = float activations, OF_BF16 (1) = __nv_bfloat16 activations;
+ *     accumulation is always fp32; statistics are accumulated in fp64
+ *   - all row strides (ld*) are in ELEMENTS
+ */
+#ifndef OCTFUSION_B200_H_
+#define OCTFUSION_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OF_F32 0
+#define OF_BF16 1
+
+#define OF_OK 0
+#define OF_E_ARG (-1)       /* inconsistent / unsupported argument combination            */
+#define OF_E_UNSUPPORTED (-2) /* shape not supported by this entry point (use the other one) */
+#define OF_E_CUDA (-3)      /* a CUDA runtime call failed (text in of_last_error)          */
+
+const char* of_last_error(void);
+int of_version(void);              /* ABI version, bumped on any signature change          */
+int of_num_sms(void);              /* multiprocessor count of the current device           */
+
+/* ------------------------------------------------------------------------------------------
+ * Tap-gather GEMM:   out[m, :] = sum_tap  mean_{j in nbr(m, tap)} [ A[j, :] | onehot(type_j) ] . W[tap]
+ *                                 (+ bias) (+ row_add[row_add_idx[m]]) (+ resid[m])
+ *
+ * One operator covers
+ *   GraphConv.forward                 models/networks/modules.py:194-220  (7 taps, mean over the
+ *                                     1/4/16 finer neighbours = scatter_mean, utils/scatter.py:42-66,
+ *                                     one-hot node type of the NEIGHBOUR appended :199-202)
+ *   Conv1x1 / nn.Linear / Conv1d k=1  modules.py:332-339, 523-525 (taps = 1, identity)
+ *   Downsample / Upsample GEMMs       modules.py:392-395, 440-443 (identity, in_rows / out_rows maps)
+ *   dense Conv3d 3^3, stride 2, and nearest-upsample+conv  modules.py:63-95, 493-502
+ *                                     (27 taps over a Morton-ordered voxel table)
+ *   the "+ emb_out[batch_id]" loop    modules.py:757-758   (row_add)
+ *   the residual / skip add           modules.py:513, 763  (resid)
+ *
+ * Neighbour table `tap_tab` [M, taps] int32 (row-major):
+ *      v >= 0 : exactly one source row v
+ *      v == -1: no neighbour (slot contributes zero; count clamps to 1, scatter.py:60)
+ *      v <= -2: several sources: o = -(v+2); tap_extra[o] = count n, tap_extra[o+1..o+n] = rows
+ *   tap_tab == NULL: identity (taps must be 1); source row = in_rows ? in_rows[m] : m
+ * A is the channel concatenation of up to two sources (a0 | a1) -- the torch.cat of the skip
+ * stack (graph_unet_hr.py:266) is never materialised.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct of_gemm_args {
+  const void* a0; int64_t lda0; int32_t c0;
+  const void* a1; int64_t lda1; int32_t c1;      /* a1 may be NULL (c1 = 0)                   */
+  const int32_t* tap_tab; const int32_t* tap_extra;
+  const int32_t* in_rows;                        /* identity mode only, may be NULL           */
+  int32_t taps;
+  const uint8_t* node_type; int32_t ntype;       /* ntype = 0: no one-hot columns             */
+  int32_t a_silu;                                /* fp32 path only: apply SiLU to A on load   */
+  /* B: fp32 path  -> canonical fp32 [K, N] row-major, K = taps*(c0+c1+ntype), k = tap*(c0+c1+ntype)+c
+   *    (exactly GraphConv.weights; other layouts go through of_repack_weight once)
+   *    tcgen05 path -> bf16 tile image produced by of_pack_weight_tc                         */
+  const void* w;
+  const float* bias;                             /* [N] or NULL                               */
+  const float* row_add; int64_t ld_row_add; const int32_t* row_add_idx;
+  const void* resid; int64_t ld_resid;           /* dtype = activation dtype                  */
+  const int32_t* out_rows;                       /* optional scatter of output rows           */
+  void* out; int64_t ldo;
+  int32_t out_f32;                               /* 1: write fp32 regardless of dtype         */
+  int32_t M, N;
+  int32_t dtype;                                 /* activation dtype of a0/a1/resid/out       */
+} of_gemm_args;
+
+/* CUDA-core FFMA path: any shape, fp32-exact accumulation order-insensitive to 1e-6. */
+int of_gather_gemm_simt(const of_gemm_args* args, void* stream);
+
+/* tcgen05 / TMEM path (bf16 operands, fp32 accumulate). Requires dtype = OF_BF16,
+ * (c0 % 64 == 0), (c1 % 64 == 0), N % 16 == 0 and w packed by of_pack_weight_tc. */
+int of_gather_gemm_tc(const of_gemm_args* args, void* stream);
+/* size in bytes of the packed image for K_feat = taps*(c0+c1) feature rows + ntype one-hot rows */
+int64_t of_pack_weight_tc_bytes(int32_t taps, int32_t c, int32_t ntype, int32_t N);
+/* w_canonical: fp32 [taps*(c+ntype), N]; out: packed bf16 image */
+int of_pack_weight_tc(const float* w_canonical, int32_t taps, int32_t c, int32_t ntype, int32_t N,
+                      void* out, void* stream);
+
+/* dst[(tap*c + ci)*N + n] = src[tap*s_tap + ci*s_c + n*s_n]   (element strides).
+ * nn.Linear [N,K]: taps=1,s_c=1,s_n=K.  Conv3d [N,C,27]: s_tap=1,s_c=27,s_n=27*C.
+ * Downsample [C,C,8] (modules.py:393): taps=1, c=8C, s_c=1, s_n=8C.                        */
+int of_repack_weight(const float* src, int64_t s_tap, int64_t s_c, int64_t s_n,
+                     int32_t taps, int32_t c, int32_t N, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Group normalisation over ragged per-sample node sets
+ *   DualOctreeGroupNorm.forward   models/networks/modules.py:291-326  (count_eps = 1e-5: eps is
+ *                                 added to the element count :302 as well as to the variance :310)
+ *   GroupNorm32 (dense)           modules.py:26-28                    (count_eps = 0)
+ * followed (fused) by SiLU (modules.py:743, 760, graph_unet_hr.py:272) and the channel concat.
+ * x is the virtual concatenation (x0 | x1).  sample_id [rows] int32 (NULL => row / rows_per_sample).
+ *   stats:    sums [B, G, 2] fp64 += (sum x, sum x^2)           (caller zeroes `sums`)
+ *   finalize: scale/shift [B, C] fp32 from sums, gamma, beta, counts
+ *   apply:    y[r, c] = act(x[r, c] * scale[b, c] + shift[b, c])   act: 0 none, 1 SiLU
+ * ------------------------------------------------------------------------------------------ */
+int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
+                const int32_t* sample_id, int32_t rows_per_sample, int64_t rows, int32_t batch,
+                int32_t groups, int32_t dtype, double* sums, void* stream);
+int of_gn_finalize(const double* sums, const int32_t* rows_of_sample, int32_t rows_per_sample,
+                   const float* gamma, const float* beta, int32_t batch, int32_t channels,
+                   int32_t groups, float eps, float count_eps, float* scale, float* shift, void* stream);
+int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
+                const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
+                const float* scale, const float* shift, int32_t act, int32_t dtype,
+                void* y, int64_t ldy, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * QKVAttention.forward   models/networks/modules.py:538-547
+ * qkv [B*T, 3*C] channels-last, head-major legacy split: head h owns columns
+ * [h*3*ch, (h+1)*3*ch) = q | k | v, ch = C / heads; q and k are both scaled by ch^-1/4; softmax
+ * over keys in fp32; out [B*T, C] with column h*ch + c.
+ * ------------------------------------------------------------------------------------------ */
+int of_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int32_t batch,
+                 int32_t tokens, int32_t heads, int32_t ch, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small per-step pieces
+ * ------------------------------------------------------------------------------------------ */
+/* timestep_embedding  diffusion_networks/ldm_diffusion_util.py:171-191  ->  out [B, dim] fp32 */
+int of_timestep_embedding(const float* t, int32_t batch, int32_t dim, float max_period, float* out,
+                          void* stream);
+/* LearnedSinusoidalPosEmb.forward  modules.py:558-563  -> out [B, 2*half+1] fp32 */
+int of_learned_sinusoidal(const float* t, const float* w, int32_t batch, int32_t half, float* out,
+                          void* stream);
+/* out[b,:] += table[label[b],:]   (nn.Embedding add, graph_unet_hr.py:232-234) */
+int of_embedding_add(const float* table, const int32_t* label, int32_t batch, int32_t dim, float* out,
+                     void* stream);
+/* eps-DDIM update of sample_loop, models/octfusion_model_union.py:345-350.
+ * log_snr / log_snr_next are device scalars (so the step is graph-capturable).
+ * x (fp32, [n]) is updated in place; x_act (activation dtype copy fed to the first conv) is
+ * refreshed when not NULL. */
+int of_ddim_eps_update(float* x, const float* eps, const float* log_snr, const float* log_snr_next,
+                       int64_t n, void* x_act, int32_t act_dtype, void* stream);
+/* dtype conversion / strided row copy: dst[r, 0:c] = src[src_rows ? src_rows[r] : r, 0:c]
+ * written to row (dst_rows ? dst_rows[r] : r) */
+int of_copy_rows(const void* src, int64_t lds, int32_t src_dtype, const int32_t* src_rows,
+                 void* dst, int64_t ldd, int32_t dst_dtype, const int32_t* dst_rows,
+                 int64_t rows, int32_t c, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dual-octree graph build   models/networks/dualoctree_networks/dual_octree.py:19-63,119-239,
+ * 241-271,332-341,381-409  (DualOctree.__init__ + post_processing_for_docnn), for ONE graph depth.
+ *
+ * Inputs: the octree levels full_depth..depth: keys[d] (int64 Morton | batch<<48, sorted),
+ * children[d] (int32, -1 = leaf else rank among non-empty), node counts nnum[d].
+ * The graph at depth D has rows  [leaves of full_depth .. leaves of D-1, all nodes of D]
+ * (remap_node_idx, dual_octree.py:265-271).
+ *
+ * of_graph_count  pass 1: per (row, dir<6) slot, number of face neighbours -> tap_tab (temporarily
+ *                 the count) and per-row extra-space demand -> extra_need [rows]
+ * (exclusive scan of extra_need is done by of_exclusive_scan_i32)
+ * of_graph_fill   pass 2: final tap_tab [rows, 7] (dir 6 = self loop, dual_octree.py:241-249) and
+ *                 tap_extra; also node_type [rows] uint8 (:381-389) and batch_id [rows] int32 (:65-79)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct of_octree_levels {
+  const int64_t* keys[16];      /* indexed by depth; only full_depth..depth are read          */
+  const int32_t* children[16];
+  const int32_t* leaf_rank[16]; /* exclusive scan of (children < 0), from of_leaf_rank         */
+  int32_t nnum[16];
+  int32_t full_depth, depth, batch;
+} of_octree_levels;
+
+/* out[i] = number of j < i with in-flag set (children[j] < 0); *total_out (device) = #leaves.
+ * scratch: >= of_scan_scratch_bytes(n) bytes. */
+int64_t of_scan_scratch_bytes(int64_t n);
+int of_leaf_rank(const int32_t* children, int32_t n, int32_t* rank_out, int32_t* total_out,
+                 void* scratch, void* stream);
+int of_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* total_out,
+                          void* scratch, void* stream);
+/* leaf_idx[leaf_rank[i]] = i for leaves, nonempty_idx[children[i]] = i for the others */
+int of_compact_idx(const int32_t* children, const int32_t* leaf_rank, int32_t n,
+                   int32_t* leaf_idx, int32_t* nonempty_idx, void* stream);
+/* number of rows of the depth-D graph (host arithmetic on nnum; no device work) */
+int64_t of_graph_rows(const of_octree_levels* oct, int32_t D);
+/* pass 1: need[row*7 + dir] = words of tap_extra the slot needs (0 when it has <= 1 neighbour) */
+int of_graph_count(const of_octree_levels* oct, int32_t D, int32_t* need, void* stream);
+/* pass 2: need_off = exclusive scan of need */
+int of_graph_fill(const of_octree_levels* oct, int32_t D, const int32_t* need_off,
+                  int32_t* tap_tab, int32_t* tap_extra, uint8_t* node_type, int32_t* batch_id,
+                  void* stream);
+/* hist[v] += 1 for v = values[i] (caller zeroes hist) -- rows per sample for the norm count */
+int of_histogram_i32(const int32_t* values, int64_t n, int32_t bins, int32_t* hist, void* stream);
+/* reference-format edge list (edge_idx [2,E], edge_dir [E] int64, sorted by row*7+dir:
+ * dual_octree.py:332-341) from a tap table.  per_slot[row*taps+tap] = #edges, then edges are
+ * written at slot_off (exclusive scan of per_slot). */
+int of_graph_edge_count(const int32_t* tap_tab, const int32_t* tap_extra, int64_t slots,
+                        int32_t* per_slot, void* stream);
+int of_graph_edges(const int32_t* tap_tab, const int32_t* tap_extra, int64_t slots, int32_t taps,
+                   const int32_t* slot_off, int64_t* edge_row, int64_t* edge_col, int64_t* edge_dir,
+                   void* stream);
+
+/* Dense voxel neighbour tables in Morton order for the LR middle U-Net (graph_unet_lr.py):
+ * mode 0: 3^3 conv, same resolution `res_log2`        (Conv3d padding=1, modules.py:493-502)
+ * mode 1: 3^3 stride-2 conv, out res = in res / 2      (ConvDownsample, modules.py:80-95)
+ * mode 2: nearest x2 upsample then 3^3 conv            (ConvUpsample, modules.py:63-77)
+ * tap = (dx+1)*9 + (dy+1)*3 + (dz+1); rows = batch * 8^out_res_log2; table values are rows of
+ * the INPUT tensor (batch * 8^in_res_log2 rows), -1 outside the grid. */
+int of_dense_tap_table(int32_t mode, int32_t out_res_log2, int32_t batch, int32_t* tap_tab,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCTFUSION_B200_H_ */

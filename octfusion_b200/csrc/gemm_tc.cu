@@ -1,0 +1,568 @@
+// Tap-gather GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+//   out[m,:] = sum_tap mean_{j in nbr(m,tap)} [A[j,:] | onehot(type_j)] . W[tap]  (+bias +row_add +resid)
+//
+// This is the B200 replacement of the reference's GraphConv op sequence
+//   x[col] (aten::index) -> scatter_mean into a [7N, C] buffer -> view(N, 7C) @ W
+// (reference models/networks/modules.py:194-220, diffusion_networks/utils/scatter.py:42-66) and of
+// its dense Conv3d / Conv1x1 / Down/Upsample GEMMs (modules.py:332-339, 392-395, 440-443, 493-502).
+// The im2col buffer is never written to HBM: gather warps build each [128 x 64] bf16 A tile
+// directly in shared memory, in the 128-byte-swizzled K-major layout tcgen05.mma reads.
+//
+// One persistent CTA per SM, 448 threads, warp-specialised:
+//   warps 0-3   epilogue: tcgen05.ld of the fp32 accumulator, +bias/+emb[batch]/+residual, store
+//   warp  4     MMA issuer (one thread): tcgen05.mma 128 x BN x 16, commits release smem stages
+//   warp  5     weight loader (one thread): cp.async.bulk (TMA 1-D) of pre-swizzled [BN x 64] tiles
+//   warps 6-13  gather producers: tap table -> source rows -> (mean) -> swizzled st.shared
+// Pipelines: smem ring (full/empty mbarriers) between {gather, loader} and MMA; two TMEM
+// accumulators (full/empty mbarriers) between MMA and epilogue, so tile i+1 is computed while
+// tile i drains.
+//
+// K is consumed as 64-wide blocks ordered (channel block outer, tap inner): the 7 (or 27) taps
+// of one 64-channel slab touch the same few hundred source rows, which then sit in L1.
+// The one-hot node-type columns (modules.py:199-202) become one extra K block of per-slot
+// type fractions; the weights are re-laid once by of_pack_weight_tc.
+#include "common.cuh"
+
+namespace of {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_PROD_WARPS = 8;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;   // 448
+constexpr int TC_MAX_TAPS = 27;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (an error the host sees), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("octfusion_b200 gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t result_slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(result_slot), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, M=128, N=BN, K=16
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 in [0,14),
+// LBO>>4 in [16,30) (unused for swizzled K-major: 1), SBO>>4 in [32,46) = 1024 B between 8-row
+// groups, version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32=1 @4, a_format BF16=1 @7, b_format BF16=1 @10,
+// a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+#define OF_TMEM_LD32(taddr, r)                                                                               \
+  asm volatile(                                                                                              \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                              \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,"  \
+      "%27,%28,%29,%30,%31}, [%32];"                                                                         \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),          \
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),          \
+        "=r"(r[30]), "=r"(r[31])                                                                             \
+      : "r"(taddr)                                                                                           \
+      : "memory")
+#define OF_TMEM_LD16(taddr, r)                                                                               \
+  asm volatile(                                                                                              \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                              \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                      \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
+      : "r"(taddr)                                                                                           \
+      : "memory")
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory plan
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct TcCfg {
+  static constexpr int A_BYTES = TC_BM * 128;                       // 16 KB
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN >= 256 ? 4 : BN >= 128 ? 5 : 6;
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static constexpr int TAP_BYTES = TC_BM * TC_MAX_TAPS * 4;         // tap-table slice of the tile
+  static constexpr int AUX_BYTES = 256;                             // mbarriers + tmem slot
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + TAP_BYTES + AUX_BYTES;
+};
+
+struct TcParams {
+  of_gemm_args g;
+  int num_kb;        // K blocks per tile
+  int cblocks;       // (c0+c1)/64
+  int npad;          // N rounded up to 16 (rows per K block in the packed weight image)
+  int m_tiles, n_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stage_base = smem_base;
+  int32_t* tap_s = reinterpret_cast<int32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES);
+  const uint32_t aux = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAP_BYTES;
+  // aux layout: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem slot
+  const uint32_t bar_full = aux, bar_empty = aux + 8 * Cfg::STAGES;
+  const uint32_t bar_tfull = aux + 16 * Cfg::STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAP_BYTES + 16 * Cfg::STAGES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const of_gemm_args& g = p.g;
+  const int taps = g.taps;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == TC_EPI_WARPS && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, TC_PROD_WARPS + 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp < TC_EPI_WARPS) {
+    // =========================== epilogue ===========================
+    const int r = warp * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * BN;
+      const int as = it & 1;
+      mbar_wait(bar_tfull + 8 * as, (it >> 1) & 1);
+      tc_fence_after();
+      const int m = m0 + r;
+      const bool row_ok = m < g.M;
+      const int64_t orow = row_ok ? (g.out_rows ? (int64_t)g.out_rows[m] : (int64_t)m) : 0;
+      const float* radd = (row_ok && g.row_add) ? g.row_add + (int64_t)g.row_add_idx[m] * g.ld_row_add : nullptr;
+      const __nv_bfloat16* res =
+          (row_ok && g.resid) ? reinterpret_cast<const __nv_bfloat16*>(g.resid) + (int64_t)m * g.ld_resid : nullptr;
+      constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t acc[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c0);
+        if (CH == 32) { OF_TMEM_LD32(taddr, acc); } else { OF_TMEM_LD16(taddr, acc); }
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const int nb = n0 + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(acc[j]);
+        const bool full = (nb + CH <= g.N);
+        if (g.bias) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) if (full || nb + j < g.N) v[j] += g.bias[nb + j];
+        }
+        if (radd) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) if (full || nb + j < g.N) v[j] += radd[nb + j];
+        }
+        if (res) {
+          if (full && (g.ld_resid % 8 == 0)) {
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) {
+              float f[8];
+              bf16x8_to_f32(ldg_nc_v4(res + nb + q * 8), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) if (nb + j < g.N) v[j] += __bfloat162float(res[nb + j]);
+          }
+        }
+        if (g.out_f32) {
+          float* o = reinterpret_cast<float*>(g.out) + orow * g.ldo + nb;
+          if (full && (g.ldo % 4 == 0)) {
+#pragma unroll
+            for (int q = 0; q < CH / 4; ++q)
+              *reinterpret_cast<float4*>(o + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) if (nb + j < g.N) o[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + nb;
+          if (full && (g.ldo % 8 == 0)) {
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) *reinterpret_cast<uint4*>(o + q * 8) = f32_to_bf16x8(v + q * 8);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) if (nb + j < g.N) o[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * as);
+    }
+  } else if (warp == TC_EPI_WARPS) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(bar_tempty + 8 * as, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            umma_bf16(d_tmem, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);            // frees the smem stage when these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * as);                 // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // =========================== weight loader ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint8_t* wp = reinterpret_cast<const uint8_t*>(g.w);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t b_addr = stage_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::B_BYTES);
+          bulk_g2s(b_addr, wp + ((int64_t)kb * p.npad + n0) * 128, Cfg::B_BYTES, bar_full + 8 * stage);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =========================== gather producers ===========================
+    const int pt = threadIdx.x - (TC_EPI_WARPS + 2) * 32;           // 0..255
+    const int q = pt & 7;                                           // 16-byte chunk of the 128-byte row
+    const int rbase = pt >> 3;                                      // 0..31, rows rbase + 32*i
+    int stage = 0;
+    uint32_t phase = 0;
+    const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(g.a0);
+    const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(g.a1);
+    int last_m0 = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.n_tiles) * TC_BM;
+      if (m0 != last_m0) {
+        // stage the tap-table slice of this row tile (source row per (row, tap))
+        named_bar_sync(1, TC_PROD_WARPS * 32);                      // everyone done with the old slice
+        const int cnt = TC_BM * taps;
+        for (int i = pt; i < cnt; i += TC_PROD_WARPS * 32) {
+          const int rr = i / taps;
+          const int m = m0 + rr;
+          int32_t v = -1;
+          if (m < g.M) {
+            if (g.tap_tab) v = g.tap_tab[(int64_t)m0 * taps + i];
+            else v = g.in_rows ? g.in_rows[m] : m;
+          }
+          tap_s[i] = v;
+        }
+        named_bar_sync(1, TC_PROD_WARPS * 32);
+        last_m0 = m0;
+      }
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
+        if (kb < p.cblocks * taps) {
+          const int cb = kb / taps, tap = kb - cb * taps;
+          const int ch = cb * TC_BK;
+          const __nv_bfloat16* src;
+          int64_t ld;
+          if (ch < g.c0) { src = a0 + ch; ld = g.lda0; } else { src = a1 + (ch - g.c0); ld = g.lda1; }
+          src += q * 8;
+          int32_t t[4];
+          uint4 val[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t[i] = tap_s[(rbase + 32 * i) * taps + tap];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            val[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (t[i] >= 0) val[i] = ldg_nc_v4(src + (int64_t)t[i] * ld);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (t[i] < -1) {                                         // 4..16 finer neighbours: mean in fp32
+              const int32_t* e = g.tap_extra + (-(t[i] + 2));
+              const int n = e[0];
+              float s[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) s[j] = 0.0f;
+              for (int k = 1; k <= n; ++k) {
+                float f[8];
+                bf16x8_to_f32(ldg_nc_v4(src + (int64_t)e[k] * ld), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] += f[j];
+              }
+              const float dn = (float)n;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) s[j] = s[j] / dn;
+              val[i] = f32_to_bf16x8(s);
+            }
+            const int rr = rbase + 32 * i;
+            sts_v4(a_addr + rr * 128 + ((q ^ (rr & 7)) << 4), val[i]);
+          }
+        } else {
+          // node-type block: column tap*ntype + type holds (#neighbours of that type)/(#neighbours)
+          // = mean of the one-hot columns the reference concatenates (modules.py:199-202).
+          if (pt < TC_BM) {
+            const int rr = pt;
+            const uint32_t rowaddr = a_addr + rr * 128;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sts_v4(rowaddr + (c << 4), z);
+            for (int tap = 0; tap < taps; ++tap) {
+              const int32_t tv = tap_s[rr * taps + tap];
+              if (tv == -1) continue;
+              unsigned long long packed = 0ull;
+              int n = 1;
+              if (tv >= 0) {
+                packed = 1ull << (8 * g.node_type[tv]);
+              } else {
+                const int32_t* e = g.tap_extra + (-(tv + 2));
+                n = e[0];
+                for (int k = 1; k <= n; ++k) packed += 1ull << (8 * g.node_type[e[k]]);
+              }
+              for (int ty = 0; ty < g.ntype && ty < 8; ++ty) {
+                const int c = (int)((packed >> (8 * ty)) & 255ull);
+                if (c == 0) continue;
+                const int col = tap * g.ntype + ty;
+                const __nv_bfloat16 hv = __float2bfloat16_rn((float)c / (float)n);
+                sts_u16(rowaddr + ((((col >> 3) ^ (rr & 7)) << 4) | ((col & 7) << 1)), __bfloat16_as_ushort(hv));
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: canonical fp32 [taps*(c+ntype), N] -> bf16 image [num_kb][npad rows][64], each
+// 8-row group 128B-swizzled exactly as the MMA expects it, so a [BN x 64] tile is one contiguous
+// cp.async.bulk.  K-block order = (channel block outer, tap inner), then the node-type block.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, int taps, int c, int ntype, int N, int npad,
+                                      int num_kb, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)num_kb * npad * 64;
+  const int cblocks = c / 64;
+  const int cp = c + ntype;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 63);                       // logical k within the block
+    const int64_t rn = i >> 6;
+    const int n = (int)(rn % npad);
+    const int kb = (int)(rn / npad);
+    float v = 0.0f;
+    if (n < N) {
+      if (kb < cblocks * taps) {
+        const int cb = kb / taps, tap = kb - cb * taps;
+        v = w[((int64_t)tap * cp + cb * 64 + j) * N + n];
+      } else if (j < taps * ntype) {
+        const int tap = j / ntype, ty = j - tap * ntype;
+        v = w[((int64_t)tap * cp + c + ty) * N + n];
+      }
+    }
+    const int64_t dst = ((int64_t)kb * npad + n) * 64 + ((((j >> 3) ^ (n & 7)) << 3) | (j & 7));
+    out[dst] = __float2bfloat16_rn(v);
+  }
+}
+
+template <int BN>
+static int launch_tc(const TcParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("of_gather_gemm_tc: cudaFuncSetAttribute(%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return OF_E_CUDA;
+    }
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gather_gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  OF_LAUNCH_CHECK("of_gather_gemm_tc");
+  return OF_OK;
+}
+
+int check_gemm_args(const of_gemm_args* a, const char* who);
+
+}  // namespace of
+
+using namespace of;
+
+extern "C" int64_t of_pack_weight_tc_bytes(int32_t taps, int32_t c, int32_t ntype, int32_t N) {
+  if (taps <= 0 || c <= 0 || c % 64 != 0 || N <= 0 || ntype < 0 || taps * ntype > 64) return -1;
+  const int64_t num_kb = (int64_t)taps * (c / 64) + (ntype > 0 ? 1 : 0);
+  const int64_t npad = (N + 15) / 16 * 16;
+  return num_kb * npad * 64 * 2;
+}
+
+extern "C" int of_pack_weight_tc(const float* w_canonical, int32_t taps, int32_t c, int32_t ntype, int32_t N,
+                                 void* out, void* stream) {
+  OF_REQUIRE(w_canonical && out, "of_pack_weight_tc: null pointer");
+  OF_REQUIRE(of_pack_weight_tc_bytes(taps, c, ntype, N) > 0, "of_pack_weight_tc: unsupported shape taps=%d c=%d nt=%d N=%d",
+             taps, c, ntype, N);
+  const int num_kb = taps * (c / 64) + (ntype > 0 ? 1 : 0);
+  const int npad = (N + 15) / 16 * 16;
+  const int64_t total = (int64_t)num_kb * npad * 64;
+  int64_t want = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 32;
+  const int grid = (int)(want < cap ? want : cap);
+  pack_weight_tc_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w_canonical, taps, c, ntype, N, npad, num_kb, reinterpret_cast<__nv_bfloat16*>(out));
+  OF_LAUNCH_CHECK("of_pack_weight_tc");
+  return OF_OK;
+}
+
+extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
+  int rc = check_gemm_args(args, "of_gather_gemm_tc");
+  if (rc) return rc;
+  const of_gemm_args& a = *args;
+  if (a.dtype != OF_BF16 || a.c0 % 64 != 0 || a.c1 % 64 != 0 || a.taps > TC_MAX_TAPS || a.taps * a.ntype > 64 ||
+      a.ntype > 8 || a.a_silu) {
+    set_error("of_gather_gemm_tc: unsupported (dtype=%d c0=%d c1=%d taps=%d ntype=%d a_silu=%d)", a.dtype, a.c0, a.c1,
+              a.taps, a.ntype, a.a_silu);
+    return OF_E_UNSUPPORTED;
+  }
+  OF_REQUIRE(a.lda0 % 8 == 0 && (a.c1 == 0 || a.lda1 % 8 == 0), "of_gather_gemm_tc: lda must be a multiple of 8");
+  OF_REQUIRE(reinterpret_cast<uintptr_t>(a.a0) % 16 == 0 && reinterpret_cast<uintptr_t>(a.a1) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(a.w) % 16 == 0,
+             "of_gather_gemm_tc: a0/a1/w must be 16-byte aligned");
+  if (a.M == 0) return OF_OK;
+  TcParams p;
+  p.g = a;
+  p.cblocks = (a.c0 + a.c1) / 64;
+  p.num_kb = p.cblocks * a.taps + (a.ntype > 0 ? 1 : 0);
+  p.npad = (a.N + 15) / 16 * 16;
+  p.m_tiles = (a.M + TC_BM - 1) / TC_BM;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // widest tile that divides the padded N: fewer re-gathers of A per output column
+  if (p.npad % 256 == 0) { p.n_tiles = p.npad / 256; return launch_tc<256>(p, st); }
+  if (p.npad % 128 == 0) { p.n_tiles = p.npad / 128; return launch_tc<128>(p, st); }
+  if (p.npad % 64 == 0)  { p.n_tiles = p.npad / 64;  return launch_tc<64>(p, st); }
+  if (p.npad % 32 == 0)  { p.n_tiles = p.npad / 32;  return launch_tc<32>(p, st); }
+  p.n_tiles = p.npad / 16;
+  return launch_tc<16>(p, st);
+}

@@ -1,0 +1,263 @@
+// Group normalisation over ragged per-sample node sets, fused with SiLU and the channel concat.
+//
+// Replaces DualOctreeGroupNorm.forward (reference models/networks/modules.py:291-326: three
+// scatter_add passes, two index_select passes and six elementwise passes = ~12 HBM round trips)
+// and the dense GroupNorm32 (modules.py:26-28) by
+//   of_gn_stats     one read  of x            -> per (sample, group) sum / sum of squares (fp64)
+//   of_gn_finalize  [B, C] scale / shift table (fp64 arithmetic, fp32 result)
+//   of_gn_apply     one read + one write      -> y = SiLU(x * scale + shift), concat fused
+// HBM-bound kernels: 16-byte vector accesses, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace of {
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int N = 4; };
+template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; };
+
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T* p, float* f);
+template <>
+__device__ __forceinline__ void load_vec<float, 4>(const float* p, float* f) {
+  float4 q = *reinterpret_cast<const float4*>(p);
+  f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+}
+template <>
+__device__ __forceinline__ void load_vec<float, 1>(const float* p, float* f) { f[0] = *p; }
+template <>
+__device__ __forceinline__ void load_vec<__nv_bfloat16, 8>(const __nv_bfloat16* p, float* f) {
+  uint4 q = *reinterpret_cast<const uint4*>(p);
+  bf16x8_to_f32(q, f);
+}
+template <>
+__device__ __forceinline__ void load_vec<__nv_bfloat16, 1>(const __nv_bfloat16* p, float* f) {
+  f[0] = __bfloat162float(*p);
+}
+template <typename T, int V>
+__device__ __forceinline__ void store_vec(T* p, const float* f);
+template <>
+__device__ __forceinline__ void store_vec<float, 4>(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <>
+__device__ __forceinline__ void store_vec<float, 1>(float* p, const float* f) { *p = f[0]; }
+template <>
+__device__ __forceinline__ void store_vec<__nv_bfloat16, 8>(__nv_bfloat16* p, const float* f) {
+  *reinterpret_cast<uint4*>(p) = f32_to_bf16x8(f);
+}
+template <>
+__device__ __forceinline__ void store_vec<__nv_bfloat16, 1>(__nv_bfloat16* p, const float* f) {
+  *p = __float2bfloat16_rn(f[0]);
+}
+
+struct GnSrc {
+  const void* x0; int64_t ld0; int c0;
+  const void* x1; int64_t ld1; int c1;
+  const int32_t* sample_id; int rows_per_sample;
+  int64_t rows;
+};
+
+template <typename T, int V>
+__device__ __forceinline__ const T* src_ptr(const GnSrc& s, int64_t r, int c) {
+  return c < s.c0 ? reinterpret_cast<const T*>(s.x0) + r * s.ld0 + c
+                  : reinterpret_cast<const T*>(s.x1) + r * s.ld1 + (c - s.c0);
+}
+
+constexpr int GN_ROWS_PER_CTA = 256;
+
+// bins: dynamic smem float [batch][groups][2]
+template <typename T, int V>
+__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int batch, int groups, double* sums) {
+  extern __shared__ float bins[];
+  const int C = s.c0 + s.c1;
+  const int cpg = C / groups;
+  const int tpr = C / V;                                   // threads per row
+  const int nbins = batch * groups * 2;
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) bins[i] = 0.0f;
+  __syncthreads();
+  const int rp = blockDim.x / tpr;                         // rows in flight (>= 1 checked on host)
+  const int64_t r0 = (int64_t)blockIdx.x * GN_ROWS_PER_CTA;
+  const int64_t r1 = min(r0 + (int64_t)GN_ROWS_PER_CTA, s.rows);
+  if ((int)threadIdx.x < rp * tpr) {
+    const int cv = (threadIdx.x % tpr) * V;
+    float sum[V], sq[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { sum[i] = 0.0f; sq[i] = 0.0f; }
+    int cur_b = -1;
+    auto flush = [&]() {
+      if (cur_b < 0) return;
+      // combine channels that fall in the same group before touching shared memory
+      int g_prev = (cv) / cpg;
+      float a = 0.0f, b = 0.0f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int g = (cv + i) / cpg;
+        if (g != g_prev) {
+          atomicAdd(&bins[(cur_b * groups + g_prev) * 2], a);
+          atomicAdd(&bins[(cur_b * groups + g_prev) * 2 + 1], b);
+          a = 0.0f; b = 0.0f; g_prev = g;
+        }
+        a += sum[i]; b += sq[i];
+        sum[i] = 0.0f; sq[i] = 0.0f;
+      }
+      atomicAdd(&bins[(cur_b * groups + g_prev) * 2], a);
+      atomicAdd(&bins[(cur_b * groups + g_prev) * 2 + 1], b);
+    };
+    for (int64_t r = r0 + threadIdx.x / tpr; r < r1; r += rp) {
+      const int b = s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample);
+      if (b != cur_b) { flush(); cur_b = b; }
+      float f[V];
+      load_vec<T, V>(src_ptr<T, V>(s, r, cv), f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+    }
+    flush();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+    const float v = bins[i];
+    if (v != 0.0f) atomicAdd(&sums[i], (double)v);
+  }
+}
+
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, const int32_t* __restrict__ rows_of_sample,
+                                   int rows_per_sample, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int batch, int C, int groups, float eps,
+                                   float count_eps, float* __restrict__ scale, float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * C) return;
+  const int b = i / C, c = i - b * C;
+  const int cpg = C / groups, g = c / cpg;
+  const double n = (double)(rows_of_sample ? rows_of_sample[b] : rows_per_sample) * (double)cpg;
+  const double inv = 1.0 / (n + (double)count_eps);      // modules.py:302: eps joins the COUNT
+  const double S = sums[(b * groups + g) * 2], Q = sums[(b * groups + g) * 2 + 1];
+  const double m = S * inv;                                // modules.py:304
+  double var = (Q - 2.0 * m * S + n * m * m) * inv;        // sum (x-m)^2 * inv_count, modules.py:308
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);       // modules.py:310
+  const double ga = gamma[c];
+  scale[i] = (float)(rstd * ga);
+  shift[i] = (float)((double)beta[c] - m * rstd * ga);
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, int act, T* y,
+                                                       int64_t ldy) {
+  const int C = s.c0 + s.c1;
+  const int tpr = C / V;
+  const int64_t total = s.rows * tpr;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / tpr;
+    const int cv = (int)(idx - r * tpr) * V;
+    const int b = s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample);
+    float f[V];
+    load_vec<T, V>(src_ptr<T, V>(s, r, cv), f);
+    const float* sc = scale + (int64_t)b * C + cv;
+    const float* sh = shift + (int64_t)b * C + cv;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float v = fmaf(f[i], sc[i], sh[i]);
+      f[i] = act ? silu_f(v) : v;
+    }
+    store_vec<T, V>(y + r * ldy + cv, f);
+  }
+}
+
+static bool vec_ok(const void* p, int64_t ld, int c, int v, int esz) {
+  if (p == nullptr) return true;
+  return (c % v == 0) && (ld % v == 0) && ((reinterpret_cast<uintptr_t>(p) % (v * esz)) == 0);
+}
+
+static int check_src(const GnSrc& s, const char* who) {
+  OF_REQUIRE(s.x0 != nullptr && s.c0 > 0, "%s: x0/c0 missing", who);
+  OF_REQUIRE((s.x1 == nullptr) == (s.c1 == 0), "%s: x1/c1 inconsistent", who);
+  OF_REQUIRE(s.sample_id != nullptr || s.rows_per_sample > 0, "%s: need sample_id or rows_per_sample", who);
+  OF_REQUIRE(s.rows >= 0, "%s: negative rows", who);
+  return OF_OK;
+}
+
+}  // namespace of
+
+extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
+                           const int32_t* sample_id, int32_t rows_per_sample, int64_t rows, int32_t batch,
+                           int32_t groups, int32_t dtype, double* sums, void* stream) {
+  using namespace of;
+  GnSrc s{x0, ld0, c0, x1, ld1, c1, sample_id, rows_per_sample, rows};
+  int rc = check_src(s, "of_gn_stats");
+  if (rc) return rc;
+  const int C = c0 + c1;
+  OF_REQUIRE(groups > 0 && C % groups == 0, "of_gn_stats: C=%d not divisible by groups=%d", C, groups);
+  OF_REQUIRE(batch > 0 && sums != nullptr, "of_gn_stats: bad batch/sums");
+  OF_REQUIRE(dtype == OF_F32 || dtype == OF_BF16, "of_gn_stats: bad dtype");
+  if (rows == 0) return OF_OK;
+  const size_t smem = (size_t)batch * groups * 2 * sizeof(float);
+  OF_REQUIRE(smem <= 200 * 1024, "of_gn_stats: batch*groups too large for the shared bins (%zu B)", smem);
+  const int grid = (int)((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define OF_GN_STATS_LAUNCH(T, V)                                                                      \
+  do {                                                                                                \
+    OF_REQUIRE(C / V <= 256, "of_gn_stats: C=%d too wide", C);                                        \
+    if (smem > 48 * 1024)                                                                             \
+      cudaFuncSetAttribute(gn_stats_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    gn_stats_kernel<T, V><<<grid, 256, smem, st>>>(s, batch, groups, sums);                           \
+  } while (0)
+  if (dtype == OF_F32) {
+    if (vec_ok(x0, ld0, c0, 4, 4) && vec_ok(x1, ld1, c1, 4, 4)) OF_GN_STATS_LAUNCH(float, 4);
+    else OF_GN_STATS_LAUNCH(float, 1);
+  } else {
+    if (vec_ok(x0, ld0, c0, 8, 2) && vec_ok(x1, ld1, c1, 8, 2)) OF_GN_STATS_LAUNCH(__nv_bfloat16, 8);
+    else OF_GN_STATS_LAUNCH(__nv_bfloat16, 1);
+  }
+#undef OF_GN_STATS_LAUNCH
+  OF_LAUNCH_CHECK("of_gn_stats");
+  return OF_OK;
+}
+
+extern "C" int of_gn_finalize(const double* sums, const int32_t* rows_of_sample, int32_t rows_per_sample,
+                              const float* gamma, const float* beta, int32_t batch, int32_t channels,
+                              int32_t groups, float eps, float count_eps, float* scale, float* shift,
+                              void* stream) {
+  using namespace of;
+  OF_REQUIRE(sums && gamma && beta && scale && shift, "of_gn_finalize: null pointer");
+  OF_REQUIRE(groups > 0 && channels % groups == 0, "of_gn_finalize: bad groups");
+  OF_REQUIRE(rows_of_sample != nullptr || rows_per_sample > 0, "of_gn_finalize: need a row count");
+  const int n = batch * channels;
+  gn_finalize_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      sums, rows_of_sample, rows_per_sample, gamma, beta, batch, channels, groups, eps, count_eps, scale, shift);
+  OF_LAUNCH_CHECK("of_gn_finalize");
+  return OF_OK;
+}
+
+extern "C" int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
+                           const int32_t* sample_id, int32_t rows_per_sample, int64_t rows, const float* scale,
+                           const float* shift, int32_t act, int32_t dtype, void* y, int64_t ldy, void* stream) {
+  using namespace of;
+  GnSrc s{x0, ld0, c0, x1, ld1, c1, sample_id, rows_per_sample, rows};
+  int rc = check_src(s, "of_gn_apply");
+  if (rc) return rc;
+  OF_REQUIRE(scale && shift && y, "of_gn_apply: null pointer");
+  OF_REQUIRE(dtype == OF_F32 || dtype == OF_BF16, "of_gn_apply: bad dtype");
+  if (rows == 0) return OF_OK;
+  const int C = c0 + c1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int sms = num_sms();
+#define OF_GN_APPLY_LAUNCH(T, V)                                                              \
+  do {                                                                                        \
+    int64_t total = rows * (C / V);                                                           \
+    int64_t want = (total + 255) / 256;                                                       \
+    int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);                    \
+    gn_apply_kernel<T, V><<<grid, 256, 0, st>>>(s, scale, shift, act, reinterpret_cast<T*>(y), ldy); \
+  } while (0)
+  if (dtype == OF_F32) {
+    if (vec_ok(x0, ld0, c0, 4, 4) && vec_ok(x1, ld1, c1, 4, 4) && vec_ok(y, ldy, C, 4, 4)) OF_GN_APPLY_LAUNCH(float, 4);
+    else OF_GN_APPLY_LAUNCH(float, 1);
+  } else {
+    if (vec_ok(x0, ld0, c0, 8, 2) && vec_ok(x1, ld1, c1, 8, 2) && vec_ok(y, ldy, C, 8, 2)) OF_GN_APPLY_LAUNCH(__nv_bfloat16, 8);
+    else OF_GN_APPLY_LAUNCH(__nv_bfloat16, 1);
+  }
+#undef OF_GN_APPLY_LAUNCH
+  OF_LAUNCH_CHECK("of_gn_apply");
+  return OF_OK;
+}
