@@ -39,6 +39,7 @@ extern "C" {
 const char* of_last_error(void);
 int of_version(void);              /* ABI version, bumped on any signature change          */
 int of_num_sms(void);              /* multiprocessor count of the current device           */
+unsigned long long of_launch_count(void); /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------
  * Tap-gather GEMM:   out[m, :] = sum_tap  mean_{j in nbr(m, tap)} [ A[j, :] | onehot(type_j) ] . W[tap]

@@ -89,13 +89,19 @@ extern "C" int of_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t 
   dim3 grid(batch * heads, (tokens + ATT_QTILE - 1) / ATT_QTILE);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == OF_F32) {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t cfg_f32 = 48 * 1024;
+    if (smem > cfg_f32) {
+      cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      cfg_f32 = 220 * 1024;
+    }
     attention_kernel<float><<<grid, ATT_WARPS * 32, smem, st>>>((const float*)qkv, ld_qkv, (float*)out, ld_out, tokens,
                                                                 heads, ch);
   } else {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t cfg_bf16 = 48 * 1024;
+    if (smem > cfg_bf16) {
+      cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      cfg_bf16 = 220 * 1024;
+    }
     attention_kernel<__nv_bfloat16><<<grid, ATT_WARPS * 32, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv,
                                                                         (__nv_bfloat16*)out, ld_out, tokens, heads, ch);
   }

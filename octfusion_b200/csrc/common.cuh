@@ -26,9 +26,11 @@ void set_error(const char* fmt, ...);
       ::of::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));  \
       return OF_E_CUDA;                                                         \
     }                                                                           \
+    ::of::add_launches(1);                                                      \
   } while (0)
 
 int num_sms();
+void add_launches(int n);   // kernel-launch counter behind of_launch_count()
 
 template <typename T> struct Elem;
 template <> struct Elem<float> {

@@ -126,6 +126,7 @@ static int run_scan(const int32_t* in, int32_t* out, int64_t n, int32_t* total_o
   if (nb > 0) scan_local_kernel<MODE><<<nb, SCAN_T, 0, st>>>(in, out, n, sums);
   scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, total_out, out + n);
   if (nb > 0) scan_add_kernel<<<nb, SCAN_T, 0, st>>>(out, n, sums);
+  if (nb > 0) add_launches(2);
   OF_LAUNCH_CHECK(who);
   return OF_OK;
 }
@@ -364,6 +365,7 @@ extern "C" int of_graph_count(const of_octree_levels* oct, int32_t D, int32_t* n
     const int64_t n = (int64_t)g.nnum[d] * 6;
     if (n == 0) continue;
     graph_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, d, need);
+    if (d > g.fd) add_launches(1);
   }
   OF_LAUNCH_CHECK("of_graph_count");
   return OF_OK;
@@ -381,6 +383,7 @@ extern "C" int of_graph_fill(const of_octree_levels* oct, int32_t D, const int32
     if (n == 0) continue;
     graph_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, d, need_off, tap_tab, tap_extra, node_type,
                                                                   batch_id);
+    if (d > g.fd) add_launches(1);
   }
   OF_LAUNCH_CHECK("of_graph_fill");
   return OF_OK;

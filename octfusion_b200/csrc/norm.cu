@@ -199,8 +199,11 @@ extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* 
 #define OF_GN_STATS_LAUNCH(T, V)                                                                      \
   do {                                                                                                \
     OF_REQUIRE(C / V <= 256, "of_gn_stats: C=%d too wide", C);                                        \
-    if (smem > 48 * 1024)                                                                             \
-      cudaFuncSetAttribute(gn_stats_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    static size_t cfg = 48 * 1024;                                                                    \
+    if (smem > cfg) {                                                                                 \
+      cudaFuncSetAttribute(gn_stats_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      cfg = 200 * 1024;                                                                               \
+    }                                                                                                 \
     gn_stats_kernel<T, V><<<grid, 256, smem, st>>>(s, batch, groups, sums);                           \
   } while (0)
   if (dtype == OF_F32) {

@@ -21,8 +21,11 @@ int num_sms() {
   }
   return cached[dev];
 }
+static unsigned long long g_launches = 0;
+void add_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 }  // namespace of
 
+extern "C" unsigned long long of_launch_count(void) { return __atomic_load_n(&of::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* of_last_error(void) { return of::g_err; }
 extern "C" int of_version(void) { return 1; }
 extern "C" int of_num_sms(void) { return of::num_sms(); }

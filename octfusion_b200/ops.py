@@ -1,0 +1,236 @@
+"""Functional layer over the C ABI: torch tensors in, torch tensors out, every arithmetic
+operation executed by a kernel of liboctfusion_b200.so on the current CUDA stream.
+
+torch is used for device memory (torch.empty / zeros), streams and nothing else.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+import torch
+
+from . import _lib
+from ._lib import lib, ptr, stream, check, dt, GemmArgs
+
+_FORCE_SIMT = os.environ.get('OCTFUSION_B200_FORCE_SIMT', '0') == '1'
+
+
+def set_force_simt(flag: bool):
+    """Debug switch: route every GEMM through the CUDA-core kernel."""
+    global _FORCE_SIMT
+    _FORCE_SIMT = bool(flag)
+
+
+class TapTable:
+    """Neighbour table of the tap-gather GEMM (see include/octfusion_b200.h)."""
+    __slots__ = ('tab', 'extra', 'taps', 'rows')
+
+    def __init__(self, tab: torch.Tensor, extra, taps: int):
+        assert tab.dtype == torch.int32 and tab.is_contiguous()
+        self.tab, self.extra, self.taps = tab, extra, taps
+        self.rows = tab.numel() // taps
+
+
+class PreparedWeight:
+    """A GEMM weight in the two layouts the kernels read:
+    canonical fp32 [taps*(c+ntype), N] (CUDA-core path) and the bf16 swizzled tile image (tcgen05
+    path, built lazily by of_pack_weight_tc).  Rebuilt when the source parameter changes."""
+
+    def __init__(self, taps: int, c: int, ntype: int, n: int):
+        self.taps, self.c, self.ntype, self.n = taps, c, ntype, n
+        self.canon = None
+        self._packed = None
+        self._src_key = None
+
+    def refresh(self, param: torch.Tensor, layout: str):
+        """layout: 'canon' ([K,N], GraphConv.weights / Upsample flat view), 'linear' ([N,K]: nn.Linear,
+        Conv1d k=1, Downsample flat view), 'conv3d' ([N,C,3,3,3])."""
+        key = (param.data_ptr(), param._version, str(param.device))
+        if key == self._src_key and self.canon is not None:
+            return self
+        _lib.require_cuda(param)
+        src = param.detach().to(torch.float32).contiguous()
+        k = self.taps * (self.c + self.ntype)
+        if layout == 'canon':
+            assert src.numel() == k * self.n, (src.shape, k, self.n)
+            self.canon = src.reshape(k, self.n)
+        else:
+            dst = torch.empty((k, self.n), dtype=torch.float32, device=src.device)
+            if layout == 'linear':
+                assert self.taps == 1 and self.ntype == 0 and src.numel() == k * self.n
+                args = (1, 1, k)
+            elif layout == 'conv3d':
+                assert self.ntype == 0 and src.numel() == k * self.n
+                args = (1, self.taps, self.taps * self.c)
+            else:
+                raise ValueError(layout)
+            check(lib.of_repack_weight(ptr(src), args[0], args[1], args[2], self.taps, self.c, self.n,
+                                       ptr(dst), stream()), 'of_repack_weight')
+            self.canon = dst
+        self._packed = None
+        self._src_key = key
+        return self
+
+    def tc_ok(self) -> bool:
+        return self.c % 64 == 0 and self.taps * self.ntype <= 64 and self.ntype <= 8 and self.taps <= 27
+
+    def packed(self):
+        if self._packed is None:
+            nbytes = lib.of_pack_weight_tc_bytes(self.taps, self.c, self.ntype, self.n)
+            if nbytes <= 0:
+                raise RuntimeError('weight shape not packable for the tcgen05 path')
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.canon.device)
+            check(lib.of_pack_weight_tc(ptr(self.canon), self.taps, self.c, self.ntype, self.n, ptr(buf), stream()),
+                  'of_pack_weight_tc')
+            self._packed = buf
+        return self._packed
+
+
+def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows=None, node_type=None,
+                a_silu=False, bias=None, row_add=None, row_add_idx=None, resid=None, out_rows=None,
+                out=None, ldo=None, out_f32=False, m=None, force_simt=False):
+    """out[m,:] = sum_tap mean_nbr [a0|a1|onehot] . W[tap] + bias + row_add[row_add_idx[m]] + resid[m]."""
+    _lib.require_cuda(a0, a1, bias, row_add, resid, out)
+    assert a0.dim() == 2 and a0.stride(1) == 1
+    c0 = a0.shape[1]
+    c1 = 0 if a1 is None else a1.shape[1]
+    assert c0 + c1 == w.c, 'channel mismatch: %d + %d vs %d' % (c0, c1, w.c)
+    if a1 is not None:
+        assert a1.dtype == a0.dtype and a1.stride(1) == 1
+    taps = 1 if tap is None else tap.taps
+    assert taps == w.taps
+    if m is None:
+        m = tap.rows if tap is not None else (in_rows.numel() if in_rows is not None else a0.shape[0])
+    n = w.n
+    act_dtype = a0.dtype
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32 if out_f32 else act_dtype, device=a0.device)
+    if ldo is None:
+        ldo = out.stride(0)
+    if resid is not None:
+        assert resid.dtype == act_dtype and resid.stride(1) == 1
+    if w.ntype > 0:
+        assert node_type is not None and node_type.dtype == torch.uint8
+    use_tc = (not _FORCE_SIMT and not force_simt and act_dtype == torch.bfloat16 and w.tc_ok() and c0 % 64 == 0
+              and c1 % 64 == 0 and not a_silu and m >= 1)
+    g = GemmArgs()
+    g.a0, g.lda0, g.c0 = a0.data_ptr(), a0.stride(0), c0
+    g.a1, g.lda1, g.c1 = (a1.data_ptr(), a1.stride(0), c1) if a1 is not None else (None, 0, 0)
+    g.tap_tab = tap.tab.data_ptr() if tap is not None else None
+    g.tap_extra = tap.extra.data_ptr() if (tap is not None and tap.extra is not None) else None
+    g.in_rows = in_rows.data_ptr() if in_rows is not None else None
+    g.taps = taps
+    g.node_type = node_type.data_ptr() if (node_type is not None and w.ntype > 0) else None
+    g.ntype = w.ntype
+    g.a_silu = 1 if a_silu else 0
+    g.w = (w.packed() if use_tc else w.canon).data_ptr()
+    g.bias = bias.data_ptr() if bias is not None else None
+    if row_add is not None:
+        assert row_add.dtype == torch.float32 and row_add_idx is not None and row_add_idx.dtype == torch.int32
+        g.row_add, g.ld_row_add, g.row_add_idx = row_add.data_ptr(), row_add.stride(0), row_add_idx.data_ptr()
+    else:
+        g.row_add, g.ld_row_add, g.row_add_idx = None, 0, None
+    g.resid, g.ld_resid = (resid.data_ptr(), resid.stride(0)) if resid is not None else (None, 0)
+    g.out_rows = out_rows.data_ptr() if out_rows is not None else None
+    g.out, g.ldo = out.data_ptr(), ldo
+    g.out_f32 = 1 if (out_f32 or (out.dtype == torch.float32 and act_dtype != torch.float32)) else 0
+    g.M, g.N = m, n
+    g.dtype = dt(a0)
+    if use_tc:
+        check(lib.of_gather_gemm_tc(C.byref(g), stream()), 'of_gather_gemm_tc')
+    else:
+        check(lib.of_gather_gemm_simt(C.byref(g), stream()), 'of_gather_gemm_simt')
+    return out
+
+
+def group_norm(x0, gamma, beta, groups: int, batch: int, *, x1=None, sample_id=None, rows_per_sample=0,
+               rows_of_sample=None, eps=1e-5, count_eps=0.0, act=False, out=None):
+    """(x0|x1) -> act(groupnorm) with per-sample statistics; stats in fp64, one read + one read/write."""
+    _lib.require_cuda(x0, x1, gamma, beta, out)
+    rows = x0.shape[0]
+    c0 = x0.shape[1]
+    c1 = 0 if x1 is None else x1.shape[1]
+    c = c0 + c1
+    dev = x0.device
+    sums = torch.zeros((batch, groups, 2), dtype=torch.float64, device=dev)
+    a1 = (ptr(x1), x1.stride(0), c1) if x1 is not None else (None, 0, 0)
+    sid = ptr(sample_id) if sample_id is not None else None
+    check(lib.of_gn_stats(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, batch, groups,
+                          dt(x0), ptr(sums), stream()), 'of_gn_stats')
+    scale = torch.empty((batch, c), dtype=torch.float32, device=dev)
+    shift = torch.empty((batch, c), dtype=torch.float32, device=dev)
+    check(lib.of_gn_finalize(ptr(sums), ptr(rows_of_sample) if rows_of_sample is not None else None, rows_per_sample,
+                             ptr(gamma), ptr(beta), batch, c, groups, float(eps), float(count_eps), ptr(scale),
+                             ptr(shift), stream()), 'of_gn_finalize')
+    if out is None:
+        out = torch.empty((rows, c), dtype=x0.dtype, device=dev)
+    check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, ptr(scale),
+                          ptr(shift), 1 if act else 0, dt(x0), ptr(out), out.stride(0), stream()), 'of_gn_apply')
+    return out
+
+
+def attention(qkv, batch: int, tokens: int, heads: int, out=None):
+    _lib.require_cuda(qkv)
+    c = qkv.shape[1] // 3
+    ch = c // heads
+    if out is None:
+        out = torch.empty((batch * tokens, c), dtype=qkv.dtype, device=qkv.device)
+    check(lib.of_attention(ptr(qkv), qkv.stride(0), ptr(out), out.stride(0), batch, tokens, heads, ch, dt(qkv),
+                           stream()), 'of_attention')
+    return out
+
+
+def timestep_embedding(t, dim: int, max_period: float = 10000.0):
+    _lib.require_cuda(t)
+    t = t.to(torch.float32).contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    check(lib.of_timestep_embedding(ptr(t), t.shape[0], dim, float(max_period), ptr(out), stream()),
+          'of_timestep_embedding')
+    return out
+
+
+def learned_sinusoidal(t, w):
+    _lib.require_cuda(t, w)
+    t = t.to(torch.float32).contiguous()
+    half = w.numel()
+    out = torch.empty((t.shape[0], 2 * half + 1), dtype=torch.float32, device=t.device)
+    check(lib.of_learned_sinusoidal(ptr(t), ptr(w), t.shape[0], half, ptr(out), stream()), 'of_learned_sinusoidal')
+    return out
+
+
+def embedding_add(out, table, label):
+    check(lib.of_embedding_add(ptr(table), ptr(label), out.shape[0], out.shape[1], ptr(out), stream()),
+          'of_embedding_add')
+    return out
+
+
+def copy_rows(src, dst, rows: int, c: int, *, src_rows=None, dst_rows=None):
+    check(lib.of_copy_rows(ptr(src), src.stride(0), dt(src), ptr(src_rows) if src_rows is not None else None,
+                           ptr(dst), dst.stride(0), dt(dst), ptr(dst_rows) if dst_rows is not None else None,
+                           rows, c, stream()), 'of_copy_rows')
+    return dst
+
+
+def ddim_eps_update(x, eps, log_snr, log_snr_next, x_act=None):
+    """x (fp32, in place) <- eps-DDIM step; log_snr / log_snr_next are 0-dim or 1-element device tensors."""
+    assert x.dtype == torch.float32 and eps.dtype == torch.float32 and x.is_contiguous() and eps.is_contiguous()
+    check(lib.of_ddim_eps_update(ptr(x), ptr(eps), ptr(log_snr), ptr(log_snr_next), x.numel(),
+                                 ptr(x_act) if x_act is not None else None,
+                                 dt(x_act) if x_act is not None else 0, stream()), 'of_ddim_eps_update')
+    return x
+
+
+def exclusive_scan_i32(values, out=None):
+    """returns int32 [n+1]: out[i] = sum(values[:i]), out[n] = total."""
+    n = values.numel()
+    if out is None:
+        out = torch.empty(n + 1, dtype=torch.int32, device=values.device)
+    scratch = torch.empty(max(int(lib.of_scan_scratch_bytes(n)), 8), dtype=torch.uint8, device=values.device)
+    check(lib.of_exclusive_scan_i32(ptr(values), ptr(out), n, None, ptr(scratch), stream()), 'of_exclusive_scan_i32')
+    return out
+
+
+def dense_tap_table(mode: int, out_res_log2: int, batch: int, device):
+    rows = batch * 8 ** out_res_log2
+    tab = torch.empty((rows, 27), dtype=torch.int32, device=device)
+    check(lib.of_dense_tap_table(mode, out_res_log2, batch, ptr(tab), stream()), 'of_dense_tap_table')
+    return TapTable(tab, None, 27)

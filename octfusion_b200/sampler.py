@@ -1,0 +1,102 @@
+"""The stage-2 ("hr") sampling loop: drop-in for reference models/octfusion_model_union.py
+`sample_loop` (:300-352, df_type "eps") with the log-SNR schedule of ldm_diffusion_util.py:300-309.
+
+One step = U-Net forward (epsilon prediction) + eps-DDIM update.  The dual octree is constant across
+steps, so all shapes are static: the whole step (~400 kernels) is captured once in a CUDA graph and
+replayed; the per-step scalars (log-SNR of t and t_next) live in device tensors that are refreshed before
+each replay.  The reference's per-sample Python loop (modules.py:757-758) and its ~300 ATen launches per
+step disappear.
+"""
+from __future__ import annotations
+import math
+import torch
+
+from . import ops
+
+
+def beta_linear_log_snr(t: float) -> float:
+    """reference ldm_diffusion_util.py:300-301, evaluated on the host in float64."""
+    return -math.log(math.expm1(1e-4 + 10.0 * t * t))
+
+
+def sampling_log_snr(steps: int):
+    """log-SNR at the steps+1 times linspace(1, 0, steps+1) (octfusion_model_union.py:292-298)."""
+    ts = torch.linspace(1.0, 0.0, steps + 1, dtype=torch.float32)
+    return [beta_linear_log_snr(float(t)) for t in ts]
+
+
+class HRStepper:
+    """Holds the static buffers of one (model, doctree) pair and runs denoising steps."""
+
+    def __init__(self, unet_hr, unet_lr, doctree, act_dtype=torch.bfloat16, label=None, use_cuda_graph=True):
+        self.hr, self.lr, self.doctree = unet_hr, unet_lr, doctree
+        self.act_dtype = act_dtype
+        dev = doctree.device
+        n = doctree.total_num
+        c = unet_hr.in_channels
+        self.x = torch.zeros((n, c), dtype=torch.float32, device=dev)          # the latent, always fp32
+        self.x_act = torch.zeros((n, c), dtype=act_dtype, device=dev) if act_dtype != torch.float32 else None
+        self.ts = torch.zeros(doctree.batch_size, dtype=torch.float32, device=dev)
+        self.ls = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.ls_next = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.label = label
+        self.eps = None
+        self.graph = None
+        self.use_cuda_graph = use_cuda_graph
+        self.kernels_per_step = 0
+
+    def set_latent(self, x):
+        self.x.copy_(x)
+        if self.x_act is not None:
+            ops.copy_rows(self.x, self.x_act, self.x.shape[0], self.x.shape[1])
+
+    def forward_eps(self):
+        xin = self.x if self.x_act is None else self.x_act
+        return self.hr(x=xin, doctree=self.doctree, unet_lr=self.lr, timesteps=self.ts, label=self.label,
+                       out_f32=True)
+
+    def _body(self):
+        self.eps = self.forward_eps()
+        ops.ddim_eps_update(self.x, self.eps, self.ls, self.ls_next, self.x_act)
+
+    def _set_scalars(self, log_snr, log_snr_next):
+        self.ts.fill_(log_snr)
+        self.ls.fill_(log_snr)
+        self.ls_next.fill_(log_snr_next)
+
+    def step(self, log_snr: float, log_snr_next: float):
+        from . import _lib
+        self._set_scalars(log_snr, log_snr_next)
+        if not self.use_cuda_graph:
+            c0 = _lib.launch_count()
+            self._body()
+            self.kernels_per_step = _lib.launch_count() - c0
+            return
+        if self.graph is None:
+            # eager warm-up on a side copy of the state (builds packed weights, tables, func attributes)
+            keep = self.x.clone()
+            c0 = _lib.launch_count()
+            self._body()
+            self.kernels_per_step = _lib.launch_count() - c0
+            self.set_latent(keep)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.set_latent(keep)        # capture does not execute; restore is a no-op safety
+        self.graph.replay()
+
+
+@torch.no_grad()
+def sample_loop(unet_hr, unet_lr, doctree, ddim_steps=200, label=None, noise=None, seed=0,
+                act_dtype=torch.bfloat16, use_cuda_graph=True, stepper=None):
+    """Returns the denoised latent [total_num, code_channel] fp32 (reference :300-352, 'eps' branch)."""
+    st = stepper or HRStepper(unet_hr, unet_lr, doctree, act_dtype, label, use_cuda_graph)
+    if noise is None:
+        g = torch.Generator(device=doctree.device).manual_seed(seed)
+        noise = torch.randn(st.x.shape, generator=g, device=doctree.device)
+    st.set_latent(noise)
+    ls = sampling_log_snr(ddim_steps)
+    for i in range(ddim_steps):
+        st.step(ls[i], ls[i + 1])
+    return st.x.clone()

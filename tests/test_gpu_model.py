@@ -1,0 +1,110 @@
+"""-m gpu parity of the composed operators and of the full denoising U-Net against the oracle.
+Tolerances are the north star's: 1e-3 relative (fp32), 2e-2 relative (bf16), max-abs error over max-abs
+reference value."""
+import pytest
+import torch
+
+from oracle import restate as R
+from tests.util import relerr, oracle_doctree, product_doctree, model_shapes, build_product, UNCOND, COND, SMALL
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+def _sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+@pytest.fixture(scope='module')
+def uncond():
+    shapes = model_shapes(UNCOND)
+    sd = R.seeded_state_dict(shapes, 0)
+    return sd, build_product(UNCOND, sd)
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_resblock_and_resample(uncond, dtype, tol):
+    sd, net = uncond
+    hr = net.unet_hr
+    dg, _ = oracle_doctree(2, 0)
+    doc = product_doctree(2, 0)
+    emb = _rand((2, 512), 3)
+    sub = _sub(sd, 'unet_hr.')
+    # input_blocks.1: 128->128 at depth 6 (identity skip); input_blocks.3: 128->256 at depth 5 (Conv1x1 skip)
+    for idx, d, cin in ((1, 6, 128), (3, 5, 128)):
+        n = dg.batch_id(d).shape[0]
+        x = _rand((n, cin), 10 + idx)
+        ref = R.res_block_embed(x, emb, dg, d, sub, 'input_blocks.%d.' % idx, d - 1)
+        y = hr.input_blocks[idx](x.to(DEV).to(dtype), emb.to(DEV), doc, d)
+        assert relerr(y.float().cpu(), ref) < tol, (idx, relerr(y.float().cpu(), ref))
+    # GraphDownsample 6->5 and GraphUpsample 5->6
+    x = _rand((dg.batch_id(6).shape[0], 128), 20)
+    ref = R.graph_downsample(x, dg, 6, sub['input_blocks.2.downsample.weights'], sub['input_blocks.2.conv.weights'], 4)
+    y = hr.input_blocks[2](x.to(DEV).to(dtype), doc, 6)
+    assert relerr(y.float().cpu(), ref) < tol
+    x = _rand((dg.batch_id(5).shape[0], 256), 21)
+    ref = R.graph_upsample(x, dg, 5, sub['output_blocks.4.upsample.weights'], sub['output_blocks.4.conv.weights'], 5)
+    y = hr.output_blocks[4](x.to(DEV).to(dtype), doc, 5)
+    assert relerr(y.float().cpu(), ref) < tol
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_lr_middle(uncond, dtype, tol):
+    sd, net = uncond
+    dg, _ = oracle_doctree(2, 0)
+    doc = product_doctree(2, 0)
+    lr_cfg, _ = R.split_cfg(UNCOND)
+    h = _rand((2 * 4096, 64), 5)
+    ts = torch.tensor([1.5, -0.5])
+    ref = R.lr_forward_as_middle(h, dg, ts, sd, lr_cfg)
+    y = net.unet_lr.forward_as_middle(h.to(DEV).to(dtype), doc, ts.to(DEV), None, None)
+    assert relerr(y.float().cpu(), ref) < tol
+
+
+@pytest.mark.parametrize('cfg_name', ['uncond', 'cond', 'small'])
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
+def test_full_unet_forward(cfg_name, dtype, tol):
+    cfg = {'uncond': UNCOND, 'cond': COND, 'small': SMALL}[cfg_name]
+    sd = R.seeded_state_dict(model_shapes(cfg), 1)
+    net = build_product(cfg, sd)
+    dg, _ = oracle_doctree(2, 0)
+    doc = product_doctree(2, 0)
+    lr_cfg, hr_cfg = R.split_cfg(cfg)
+    x = _rand((dg.total_num, 3), 7)
+    ts = torch.tensor([1.5, -0.5])
+    label = torch.tensor([1, 3]) if cfg.get('num_classes') else None
+    ref = R.hr_forward(x, dg, ts, sd, hr_cfg, lr_cfg, label=label)
+    y = net(unet_type='hr', x=x.to(DEV).to(dtype), doctree=doc, timesteps=ts.to(DEV), unet_lr=net.unet_lr,
+            label=label.to(DEV) if label is not None else None)
+    assert y.dtype == torch.float32
+    e = relerr(y.cpu(), ref)
+    assert e < tol, e
+
+
+def test_sampler_cuda_graph_matches_eager_and_oracle():
+    from octfusion_b200.sampler import sample_loop, sampling_log_snr
+    cfg = SMALL
+    sd = R.seeded_state_dict(model_shapes(cfg), 2)
+    net = build_product(cfg, sd)
+    dg, _ = oracle_doctree(2, 0)
+    doc = product_doctree(2, 0)
+    lr_cfg, hr_cfg = R.split_cfg(cfg)
+    steps = 4
+    noise = _rand((dg.total_num, 3), 9)
+    x = noise.clone()
+    ls = sampling_log_snr(steps)
+    for i in range(steps):
+        t = torch.full((2,), ls[i])
+        eps = R.hr_forward(x, dg, t, sd, hr_cfg, lr_cfg)
+        x = R.ddim_eps_update(x, eps, torch.tensor(ls[i]), torch.tensor(ls[i + 1]))
+    for graph in (False, True):
+        y = sample_loop(net.unet_hr, net.unet_lr, doc, ddim_steps=steps, noise=noise.to(DEV), act_dtype=torch.float32,
+                        use_cuda_graph=graph)
+        assert relerr(y.cpu(), x) < 2e-3, (graph, relerr(y.cpu(), x))
+    yb = sample_loop(net.unet_hr, net.unet_lr, doc, ddim_steps=steps, noise=noise.to(DEV), act_dtype=torch.bfloat16)
+    assert relerr(yb.cpu(), x) < 4e-2

@@ -1,0 +1,83 @@
+"""Pins the oracle (oracle/restate.py) against the UNMODIFIED reference modules imported from
+/root/reference (build container only: skipped where the reference tree is absent)."""
+import pytest
+import torch
+
+from oracle import restate as R, ref_import
+from tests.util import relerr, oracle_doctree, UNCOND, COND, SMALL
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope='module')
+def ref():
+    return ref_import.load()
+
+
+def _ref_doctree(ref, batch, seed):
+    from octfusion_b200.synth import synth_splits
+    from oracle.octree_util import octree_from_splits
+    l4, l5 = synth_splits(batch, seed)
+    doc = ref.dual_octree.DualOctree(octree_from_splits(l4, l5, batch))
+    doc.post_processing_for_docnn()
+    return doc
+
+
+@pytest.mark.parametrize('batch,seed', [(1, 0), (2, 0), (3, 5)])
+def test_dual_graph_equals_reference(ref, batch, seed):
+    doc = _ref_doctree(ref, batch, seed)
+    dg, _ = oracle_doctree(batch, seed)
+    for d in range(4, 7):
+        a, b = R.edge_set(doc.graph[d]), R.edge_set(dg.graph[d])
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert torch.equal(doc.graph[d]['node_type'], dg.graph[d]['node_type'])
+        assert torch.equal(doc.batch_id(d), dg.batch_id(d))
+    assert torch.equal(doc.nnum, dg.nnum) and torch.equal(doc.lnum, dg.lnum)
+
+
+@pytest.mark.parametrize('name', ['small', 'uncond', 'cond'])
+def test_full_unet_equals_reference(ref, name):
+    cfg = {'uncond': UNCOND, 'cond': COND, 'small': SMALL}[name]
+    net = ref.union.UNet3DModel('hr', **cfg).eval()
+    sd = R.seeded_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 1)
+    net.load_state_dict(sd)
+    batch = 1 if name != 'small' else 2
+    doc = _ref_doctree(ref, batch, 0)
+    dg, _ = oracle_doctree(batch, 0)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(doc.total_num, 3, generator=g)
+    ts = torch.tensor([1.5, -0.5])[:batch]
+    label = torch.tensor([1, 3])[:batch] if cfg.get('num_classes') else None
+    with torch.no_grad():
+        want = net(unet_type='hr', x=x, doctree=doc, timesteps=ts, unet_lr=net.unet_lr, label=label)
+    lr_cfg, hr_cfg = R.split_cfg(cfg)
+    got = R.hr_forward(x, dg, ts, sd, hr_cfg, lr_cfg, label=label)
+    assert float(want.abs().max()) > 0.1          # the seeded weights must not leave the net at zero
+    assert relerr(got, want) < 2e-5
+
+
+def test_operators_equal_reference(ref):
+    m = ref.modules
+    doc = _ref_doctree(ref, 2, 0)
+    dg, _ = oracle_doctree(2, 0)
+    g = torch.Generator().manual_seed(3)
+    # config-1 analogue: GraphConv 8->8 on the depth-4 full layer
+    conv = m.GraphConv(8, 8, 7, 7, 0)
+    x = torch.randn(2 * 4096, 8, generator=g)
+    with torch.no_grad():
+        assert relerr(R.graph_conv(x, dg.graph[4], conv.weights.data, 0), conv(x, doc, 4)) < 1e-6
+    conv = m.GraphConv(16, 24, 7, 7, 5)
+    x = torch.randn(dg.batch_id(6).shape[0], 16, generator=g)
+    with torch.no_grad():
+        assert relerr(R.graph_conv(x, dg.graph[6], conv.weights.data, 5), conv(x, doc, 6)) < 1e-6
+    for c in (24, 64, 384):
+        gn = m.DualOctreeGroupNorm(c)
+        gn.weights.data.normal_(1, 0.1, generator=g); gn.bias.data.normal_(0, 0.1, generator=g)
+        x = torch.randn(dg.batch_id(5).shape[0], c, generator=g) * 2 + 0.5
+        with torch.no_grad():
+            assert relerr(R.doctree_group_norm(x, dg.batch_id(5), 2, gn.weights.data, gn.bias.data), gn(x, doc, 5)) < 1e-5
+    qkv = torch.randn(8, 96, 64, generator=g)
+    assert relerr(R.qkv_attention(qkv), m.QKVAttention()(qkv)) < 1e-6
+    t = torch.tensor([9.2, -2.3, 0.1])
+    assert relerr(R.timestep_embedding(t, 128), ref.util.timestep_embedding(t, 128)) < 1e-6
+    assert abs(float(R.beta_linear_log_snr(torch.tensor(0.3))) - float(ref.util.beta_linear_log_snr(torch.tensor(0.3)))) < 1e-6
