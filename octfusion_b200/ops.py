@@ -12,6 +12,13 @@ from . import _lib
 from ._lib import lib, ptr, stream, check, dt, GemmArgs
 
 _FORCE_SIMT = os.environ.get('OCTFUSION_B200_FORCE_SIMT', '0') == '1'
+_PROFILE = None        # when a list: (kind, meta, start_event, end_event) per GEMM launch (bench.py roofline leg)
+
+
+def set_profile(sink):
+    """sink: a list to append per-launch CUDA-event pairs to, or None to switch profiling off."""
+    global _PROFILE
+    _PROFILE = sink
 
 
 def set_force_simt(flag: bool):
@@ -135,10 +142,24 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g.out_f32 = 1 if (out_f32 or (out.dtype == torch.float32 and act_dtype != torch.float32)) else 0
     g.M, g.N = m, n
     g.dtype = dt(a0)
+    prof = _PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     if use_tc:
         check(lib.of_gather_gemm_tc(C.byref(g), stream()), 'of_gather_gemm_tc')
     else:
         check(lib.of_gather_gemm_simt(C.byref(g), stream()), 'of_gather_gemm_simt')
+    if prof is not None:
+        e1.record()
+        es = 2 if act_dtype == torch.bfloat16 else 4
+        k = taps * (c0 + c1 + w.ntype)
+        nnz = 0 if tap is None else tap.rows * taps          # table entries read (4 B each)
+        prof.append(dict(kind='tc' if use_tc else 'simt', M=m, N=n, K=k, taps=taps, c=c0 + c1, ntype=w.ntype,
+                         flops=2.0 * m * k * n,
+                         bytes=float(m * (c0 + c1) * es + m * n * (4 if g.out_f32 else es) + nnz * 4 + k * n * es
+                                     + (m * n * es if resid is not None else 0)),
+                         start=e0, end=e1))
     return out
 
 
@@ -222,6 +243,8 @@ def ddim_eps_update(x, eps, log_snr, log_snr_next, x_act=None):
 def exclusive_scan_i32(values, out=None):
     """returns int32 [n+1]: out[i] = sum(values[:i]), out[n] = total."""
     n = values.numel()
+    if n == 0:
+        return torch.zeros(1, dtype=torch.int32, device=values.device)
     if out is None:
         out = torch.empty(n + 1, dtype=torch.int32, device=values.device)
     scratch = torch.empty(max(int(lib.of_scan_scratch_bytes(n)), 8), dtype=torch.uint8, device=values.device)

@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE.  Regenerates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported under the ocnn shim) on seeded inputs.  Run in the build container:
+
+    python -m oracle.gen_golden
+
+The fixtures travel to the GPU box (where the reference tree does not exist) and pin both the oracle
+(`-m "not gpu"`) and the CUDA path (`-m gpu`).  Inputs are regenerated from seeds by the tests; the stored
+input checksums guard against a drifting generator.
+"""
+import os
+import sys
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import, restate as R                      # noqa: E402
+from oracle.octree_util import octree_from_splits                # noqa: E402
+from octfusion_b200.synth import synth_splits                    # noqa: E402
+from tests.util import UNCOND, SMALL, COND                       # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def checksum(t: torch.Tensor) -> float:
+    return float(t.double().abs().sum())
+
+
+def seeded_inputs(n, c, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, c, generator=g)
+
+
+def main():
+    ref = ref_import.load()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_grad_enabled(False)
+
+    def ref_doctree(batch, seed):
+        l4, l5 = synth_splits(batch, seed)
+        doc = ref.dual_octree.DualOctree(octree_from_splits(l4, l5, batch))
+        doc.post_processing_for_docnn()
+        return doc
+
+    # 1. dual graph of one shape: canonical sorted (row*7+dir, col) per depth
+    doc = ref_doctree(1, 0)
+    g = {}
+    for d in range(4, 7):
+        k, c = R.edge_set(doc.graph[d])
+        g['key%d' % d], g['col%d' % d] = k.numpy().astype(np.int32), c.numpy().astype(np.int32)
+        g['node_type%d' % d] = doc.graph[d]['node_type'].numpy().astype(np.uint8)
+        g['batch_id%d' % d] = doc.batch_id(d).numpy().astype(np.int32)
+    g['nnum'], g['lnum'] = doc.nnum.numpy(), doc.lnum.numpy()
+    np.savez_compressed(os.path.join(OUT, 'dual_graph_b1_s0.npz'), **g)
+
+    # 2. BASELINE.json configs[0] analogue: one GraphConv 8->8 on the depth-4 full layer of one octree
+    conv = ref.modules.GraphConv(8, 8, 7, 7, 0)
+    w = seeded_inputs(56, 8, 11) / np.sqrt(56.0)
+    conv.weights.data.copy_(w)
+    x = seeded_inputs(4096, 8, 12)
+    np.savez_compressed(os.path.join(OUT, 'graphconv_config1.npz'), x=x.numpy(), w=w.numpy(),
+                        y=conv(x, doc, 4).numpy())
+
+    # 3. operators at depth 6 with node types / ragged norm / attention
+    conv = ref.modules.GraphConv(64, 32, 7, 7, 5)
+    w = seeded_inputs(7 * 69, 32, 13) / np.sqrt(7 * 69.0)
+    conv.weights.data.copy_(w)
+    n6 = doc.total_num
+    x = seeded_inputs(n6, 64, 14)
+    ops = {'conv_y': conv(x, doc, 6)[::16].numpy(),      # every 16th row keeps the fixture small
+            'conv_x_sum': checksum(x), 'conv_w_sum': checksum(w)}
+    gn = ref.modules.DualOctreeGroupNorm(64)
+    gam, bet = 1 + 0.1 * seeded_inputs(1, 64, 15), 0.1 * seeded_inputs(1, 64, 16)
+    gn.weights.data.copy_(gam); gn.bias.data.copy_(bet)
+    doc2 = ref_doctree(2, 0)
+    x2 = seeded_inputs(doc2.batch_id(5).shape[0], 64, 17) * 2 + 0.5
+    ops['gn_y'] = gn(x2, doc2, 5)[::16].numpy()
+    qkv = seeded_inputs(8 * 96, 64, 18).reshape(8, 96, 64)
+    ops['attn_y'] = ref.modules.QKVAttention()(qkv).numpy()
+    np.savez_compressed(os.path.join(OUT, 'operators.npz'), **ops)
+
+    # 4. full U-Net forwards (weights from the shared seeded_state_dict)
+    for name, cfg, batch in (('small', SMALL, 2), ('uncond', UNCOND, 1), ('cond', COND, 1)):
+        net = ref.union.UNet3DModel('hr', **cfg).eval()
+        sd = R.seeded_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 1)
+        net.load_state_dict(sd)
+        d = ref_doctree(batch, 0)
+        x = seeded_inputs(d.total_num, 3, 7)
+        ts = torch.tensor([1.5, -0.5])[:batch]
+        label = torch.tensor([1, 3])[:batch] if cfg.get('num_classes') else None
+        y = net(unet_type='hr', x=x, doctree=d, timesteps=ts, unet_lr=net.unet_lr, label=label)
+        np.savez_compressed(os.path.join(OUT, 'unet_%s.npz' % name), y=y.numpy(), x_sum=checksum(x),
+                            w_sum=sum(checksum(v) for v in sd.values()), batch=batch)
+        print(name, 'out absmax', float(y.abs().max()), 'N', d.total_num)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KB')
+
+
+if __name__ == '__main__':
+    main()

@@ -108,3 +108,46 @@ def test_sampler_cuda_graph_matches_eager_and_oracle():
         assert relerr(y.cpu(), x) < 2e-3, (graph, relerr(y.cpu(), x))
     yb = sample_loop(net.unet_hr, net.unet_lr, doc, ddim_steps=steps, noise=noise.to(DEV), act_dtype=torch.bfloat16)
     assert relerr(yb.cpu(), x) < 4e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# against the committed golden vectors (outputs of the unmodified reference, tests/golden/)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['small', 'uncond', 'cond'])
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
+def test_unet_against_reference_golden(name, dtype, tol):
+    import os
+    import numpy as np
+    from tests.util import GOLDEN
+    cfg = {'uncond': UNCOND, 'cond': COND, 'small': SMALL}[name]
+    g = np.load(os.path.join(GOLDEN, 'unet_%s.npz' % name))
+    batch = int(g['batch'])
+    sd = R.seeded_state_dict(model_shapes(cfg), 1)
+    net = build_product(cfg, sd)
+    doc = product_doctree(batch, 0)
+    x = _rand((doc.total_num, 3), 7)
+    ts = torch.tensor([1.5, -0.5])[:batch]
+    label = torch.tensor([1, 3])[:batch].to(DEV) if cfg.get('num_classes') else None
+    y = net(unet_type='hr', x=x.to(DEV).to(dtype), doctree=doc, timesteps=ts.to(DEV), unet_lr=net.unet_lr, label=label)
+    e = relerr(y.cpu(), torch.from_numpy(g['y']))
+    assert e < tol, e
+
+
+def test_graph_and_config1_against_reference_golden():
+    import os
+    import numpy as np
+    from tests.util import GOLDEN
+    from octfusion_b200.modules import GraphConv
+    doc = product_doctree(1, 0)
+    g = np.load(os.path.join(GOLDEN, 'dual_graph_b1_s0.npz'))
+    for d in range(4, 7):
+        k, c = R.edge_set({'edge_idx': doc.graph[d]['edge_idx'].cpu(), 'edge_dir': doc.graph[d]['edge_dir'].cpu()})
+        assert np.array_equal(k.numpy(), g['key%d' % d].astype(np.int64))
+        assert np.array_equal(c.numpy(), g['col%d' % d].astype(np.int64))
+        assert np.array_equal(doc.plan[d].node_type.cpu().numpy(), g['node_type%d' % d])
+        assert np.array_equal(doc.plan[d].batch_id.cpu().numpy(), g['batch_id%d' % d])
+    g = np.load(os.path.join(GOLDEN, 'graphconv_config1.npz'))
+    conv = GraphConv(8, 8, 7, 7, 0)
+    conv.weights.data.copy_(torch.from_numpy(g['w']))
+    y = conv.to(DEV)(torch.from_numpy(g['x']).to(DEV), doc, 4)
+    assert relerr(y.cpu(), torch.from_numpy(g['y'])) < 1e-5

@@ -1,0 +1,121 @@
+"""CPU tests (-m "not gpu") of everything that does not need a device: the C-ABI library loads and
+exports every symbol include/octfusion_b200.h declares, state_dict parity with the reference, the synthetic
+workload generator, the sharding rule, and the loud failure when no CUDA device is present."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import pytest
+import torch
+
+from tests.util import UNCOND, COND, SMALL, model_shapes
+from oracle import restate as R, ref_import
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from octfusion_b200 import _lib, build
+    hdr = open(os.path.join(ROOT, 'include', 'octfusion_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(of_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(build.LIB)
+    for name in declared:
+        assert hasattr(lib, name), 'library does not export %s' % name
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.of_version() == 1
+
+
+def test_argument_validation_without_gpu():
+    """negative return + error text, no launch, no crash."""
+    from octfusion_b200 import _lib
+    g = _lib.GemmArgs()
+    assert _lib.lib.of_gather_gemm_simt(ctypes.byref(g), None) == -1
+    assert b'of_gather_gemm_simt' in _lib.lib.of_last_error()
+    assert _lib.lib.of_pack_weight_tc_bytes(7, 100, 5, 128) == -1          # c not a multiple of 64
+    assert _lib.lib.of_pack_weight_tc_bytes(7, 128, 5, 128) == (7 * 2 + 1) * 128 * 64 * 2
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip('only meaningful on a host without a GPU')
+    from octfusion_b200 import octree_from_splits, DualOctree
+    from octfusion_b200.modules import GraphConv
+    from octfusion_b200.synth import synth_splits
+    l4, l5 = synth_splits(1, 0)
+    with pytest.raises(RuntimeError):
+        DualOctree(octree_from_splits(l4, l5, 1, device='cpu'))
+    conv = GraphConv(8, 8, 7, 7, 0)
+
+    class _Plan:  # a plan on the CPU must be refused, not silently computed
+        tap = None
+        node_type = None
+    with pytest.raises(Exception):
+        conv.run(torch.zeros(4, 8), _Plan())
+
+
+@pytest.mark.parametrize('cfg', [UNCOND, COND, SMALL])
+def test_hr_layout_matches_module_tree(cfg):
+    shapes = model_shapes(cfg)
+    _, hr = R.split_cfg(cfg)
+    seq_in, _, seq_out = R.hr_layout(hr)
+    for kind, p, _, _ in seq_in + seq_out:
+        key = {'conv': 'weights', 'res': 'conv1.weights', 'down': 'downsample.weights', 'up': 'upsample.weights'}[kind]
+        assert 'unet_hr.' + p + key in shapes
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize('cfg', [UNCOND, COND])
+def test_state_dict_parity_with_reference(cfg):
+    ref = ref_import.load()
+    want = {k: tuple(v.shape) for k, v in ref.union.UNet3DModel('hr', **cfg).state_dict().items()}
+    assert want == model_shapes(cfg)
+
+
+def test_synth_is_deterministic_and_shapenet_sized():
+    from octfusion_b200.synth import synth_splits
+    a, b = synth_splits(4, 3), synth_splits(4, 3)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    l4, l5 = synth_splits(8, 0)
+    n5, n6 = 8 * int(l4.sum()) / 8, 8 * int(l5.sum()) / 8
+    assert 4000 < n5 < 12000 and 10000 < n6 < 40000
+
+
+def test_shard_rules():
+    from octfusion_b200.shard import shard_range, strided_indices
+    for n, w in ((32, 8), (32, 3), (5, 8)):
+        cover = []
+        for r in range(w):
+            lo, hi = shard_range(n, r, w)
+            cover += list(range(lo, hi))
+        assert cover == list(range(n))
+        assert sorted(sum((strided_indices(n, r, w) for r in range(w)), [])) == list(range(n))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from octfusion_b200.shard import all_gather_latents, shard_range
+    lo, hi = shard_range(5, rank, world)
+    x = torch.arange(lo * 3, hi * 3, dtype=torch.float32).reshape(-1, 3)      # ragged: 3 vs 2 rows
+    out = torch.cat(all_gather_latents(x), 0)
+    q.put((rank, out.tolist()))
+    dist.destroy_process_group()
+
+
+def test_ragged_all_gather_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(60)
+    want = torch.arange(15, dtype=torch.float32).reshape(5, 3).tolist()
+    assert all(r[1] == want for r in res)
