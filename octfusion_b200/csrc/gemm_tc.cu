@@ -13,7 +13,8 @@
 //   warps 0-3   epilogue: tcgen05.ld of the fp32 accumulator, +bias/+emb[batch]/+residual, store
 //   warp  4     MMA issuer (one thread): tcgen05.mma 128 x BN x 16, commits release smem stages
 //   warp  5     weight loader (one thread): cp.async.bulk (TMA 1-D) of pre-swizzled [BN x 64] tiles
-//   warps 6-13  gather producers: tap table -> source rows -> (mean) -> swizzled st.shared
+//   warps 6-13  gather producers (4 groups x 2 warps, one K block each in flight):
+//               tap table -> source rows -> (mean) -> swizzled st.shared
 // Pipelines: smem ring (full/empty mbarriers) between {gather, loader} and MMA; two TMEM
 // accumulators (full/empty mbarriers) between MMA and epilogue, so tile i+1 is computed while
 // tile i drains.
@@ -32,6 +33,7 @@ constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;   // 448
 constexpr int TC_MAX_TAPS = 27;
+constexpr int TC_GROUPS = 4;                // producer groups of 2 warps
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -166,7 +168,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BN >= 256 ? 4 : BN >= 128 ? 5 : 6;
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-  static constexpr int TAP_BYTES = TC_BM * TC_MAX_TAPS * 4;         // tap-table slice of the tile
+  static constexpr int TAP_BYTES = 0;                               // (tap table is read through L1)
   static constexpr int AUX_BYTES = 256;                             // mbarriers + tmem slot
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + TAP_BYTES + AUX_BYTES;
 };
@@ -189,7 +191,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t stage_base = smem_base;
-  int32_t* tap_s = reinterpret_cast<int32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES);
   const uint32_t aux = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAP_BYTES;
   // aux layout: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem slot
   const uint32_t bar_full = aux, bar_empty = aux + 8 * Cfg::STAGES;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 
   if (warp == TC_EPI_WARPS && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, TC_PROD_WARPS + 1);
+      mbar_init(bar_full + 8 * s, TC_PROD_WARPS / TC_GROUPS + 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -341,34 +342,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     }
   } else {
     // =========================== gather producers ===========================
+    // 4 independent groups of 2 warps; group g produces the K blocks whose running index is = g mod 4,
+    // so 4 K blocks (64 KB of gathers) are in flight per SM and the memory latency of one block is
+    // hidden behind the other three.  Each thread owns one 16-byte chunk column (q) of 16 rows.
     const int pt = threadIdx.x - (TC_EPI_WARPS + 2) * 32;           // 0..255
-    const int q = pt & 7;                                           // 16-byte chunk of the 128-byte row
-    const int rbase = pt >> 3;                                      // 0..31, rows rbase + 32*i
-    int stage = 0;
-    uint32_t phase = 0;
+    const int grp = pt >> 6;                                        // producer group 0..3
+    const int gt = pt & 63;
+    const int q = gt & 7;                                           // 16-byte chunk of the 128-byte row
+    const int rbase = gt >> 3;                                      // 0..7, rows rbase + 8*i
     const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(g.a0);
     const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(g.a1);
-    int last_m0 = -1;
+    const int32_t* __restrict__ tab = g.tap_tab;
+    uint32_t kbg = 0;                                               // running K-block index of this CTA
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.n_tiles) * TC_BM;
-      if (m0 != last_m0) {
-        // stage the tap-table slice of this row tile (source row per (row, tap))
-        named_bar_sync(1, TC_PROD_WARPS * 32);                      // everyone done with the old slice
-        const int cnt = TC_BM * taps;
-        for (int i = pt; i < cnt; i += TC_PROD_WARPS * 32) {
-          const int rr = i / taps;
-          const int m = m0 + rr;
-          int32_t v = -1;
-          if (m < g.M) {
-            if (g.tap_tab) v = g.tap_tab[(int64_t)m0 * taps + i];
-            else v = g.in_rows ? g.in_rows[m] : m;
-          }
-          tap_s[i] = v;
-        }
-        named_bar_sync(1, TC_PROD_WARPS * 32);
-        last_m0 = m0;
-      }
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = 0; kb < p.num_kb; ++kb, ++kbg) {
+        if ((int)(kbg % TC_GROUPS) != grp) continue;
+        const uint32_t stage = kbg % Cfg::STAGES;
+        const uint32_t phase = (kbg / Cfg::STAGES) & 1u;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
         if (kb < p.cblocks * taps) {
@@ -378,48 +369,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           int64_t ld;
           if (ch < g.c0) { src = a0 + ch; ld = g.lda0; } else { src = a1 + (ch - g.c0); ld = g.lda1; }
           src += q * 8;
-          int32_t t[4];
-          uint4 val[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) t[i] = tap_s[(rbase + 32 * i) * taps + tap];
+          for (int half = 0; half < 2; ++half) {
+            int32_t t[8];
+            uint4 val[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            val[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (t[i] >= 0) val[i] = ldg_nc_v4(src + (int64_t)t[i] * ld);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (t[i] < -1) {                                         // 4..16 finer neighbours: mean in fp32
-              const int32_t* e = g.tap_extra + (-(t[i] + 2));
-              const int n = e[0];
-              float s[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) s[j] = 0.0f;
-              for (int k = 1; k <= n; ++k) {
-                float f[8];
-                bf16x8_to_f32(ldg_nc_v4(src + (int64_t)e[k] * ld), f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) s[j] += f[j];
-              }
-              const float dn = (float)n;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) s[j] = s[j] / dn;
-              val[i] = f32_to_bf16x8(s);
+            for (int i = 0; i < 8; ++i) {
+              const int m = m0 + rbase + 8 * (half * 8 + i);
+              int32_t v = -1;
+              if (m < g.M) v = tab ? __ldg(tab + (int64_t)m * taps + tap) : (g.in_rows ? __ldg(g.in_rows + m) : m);
+              t[i] = v;
             }
-            const int rr = rbase + 32 * i;
-            sts_v4(a_addr + rr * 128 + ((q ^ (rr & 7)) << 4), val[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              val[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (t[i] >= 0) val[i] = ldg_nc_v4(src + (int64_t)t[i] * ld);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (t[i] < -1) {                                       // 4..16 finer neighbours: mean in fp32
+                const int32_t* e = g.tap_extra + (-(t[i] + 2));
+                const int n = e[0];
+                float sacc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sacc[j] = 0.0f;
+                for (int k = 1; k <= n; ++k) {
+                  float f[8];
+                  bf16x8_to_f32(ldg_nc_v4(src + (int64_t)e[k] * ld), f);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) sacc[j] += f[j];
+                }
+                const float dn = (float)n;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sacc[j] = sacc[j] / dn;
+                val[i] = f32_to_bf16x8(sacc);
+              }
+              const int rr = rbase + 8 * (half * 8 + i);
+              sts_v4(a_addr + rr * 128 + ((q ^ (rr & 7)) << 4), val[i]);
+            }
           }
         } else {
           // node-type block: column tap*ntype + type holds (#neighbours of that type)/(#neighbours)
           // = mean of the one-hot columns the reference concatenates (modules.py:199-202).
-          if (pt < TC_BM) {
-            const int rr = pt;
+#pragma unroll 1
+          for (int rr = gt; rr < TC_BM; rr += 64) {
             const uint32_t rowaddr = a_addr + rr * 128;
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int c = 0; c < 8; ++c) sts_v4(rowaddr + (c << 4), z);
+            const int m = m0 + rr;
+            if (m >= g.M) continue;
             for (int tap = 0; tap < taps; ++tap) {
-              const int32_t tv = tap_s[rr * taps + tap];
+              const int32_t tv = tab ? __ldg(tab + (int64_t)m * taps + tap) : m;
               if (tv == -1) continue;
               unsigned long long packed = 0ull;
               int n = 1;
@@ -443,7 +444,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   }

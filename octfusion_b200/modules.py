@@ -209,6 +209,15 @@ class TimestepBlock(nn.Module):
     pass
 
 
+def _concat_rows(x0, x1):
+    """materialise (x0 | x1) -- only needed where the concatenation itself is the residual."""
+    n, c0, c1 = x0.shape[0], x0.shape[1], x1.shape[1]
+    cat = torch.empty((n, c0 + c1), dtype=x0.dtype, device=x0.device)
+    ops.copy_rows(x0, cat, n, c0)
+    ops.copy_rows(x1, cat[:, c0:], n, c1)
+    return cat
+
+
 class GraphResBlockEmbed(TimestepBlock):
     """reference modules.py:661-763.  GN -> SiLU -> conv1 -> + Linear(SiLU(emb))[batch] -> GN -> SiLU ->
     conv2 -> + skip(x).  Fusions: GN-apply+SiLU (+ the channel concat of the skip stack) in one pass,
@@ -245,9 +254,10 @@ class GraphResBlockEmbed(TimestepBlock):
         h = self.block2_norm.run(h, plan, batch_size, act=True)
         if isinstance(self.skip_connection, Conv1x1):
             skip = self.skip_connection.run(x0, x1)
-        else:
-            assert x1 is None
+        elif x1 is None:
             skip = x0
+        else:
+            skip = _concat_rows(x0, x1)          # identity skip of a concatenated input (e.g. 256+256 -> 512)
         return self.conv2.run(h, plan, resid=skip)
 
     @torch.no_grad()
@@ -436,8 +446,7 @@ class ResnetBlock(nn.Module):
         h = self.block1[2].run(h, tap, row_add=t, row_add_idx=tables.sample_id(res_log2))
         h = self.block2[0].run(h, b, v, act=True)
         if isinstance(self.res_conv, nn.Identity):
-            assert x1 is None
-            skip = x0
+            skip = x0 if x1 is None else _concat_rows(x0, x1)
         else:
             skip = ops.gather_gemm(x0, self.res_conv.prepared(), a1=x1, bias=self.res_conv.bias)
         return self.block2[3].run(h, tap, resid=skip)
