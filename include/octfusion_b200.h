@@ -168,9 +168,10 @@ int of_copy_rows(const void* src, int64_t lds, int32_t src_dtype, const int32_t*
  * The graph at depth D has rows  [leaves of full_depth .. leaves of D-1, all nodes of D]
  * (remap_node_idx, dual_octree.py:265-271).
  *
- * of_graph_count  pass 1: per (row, dir<6) slot, number of face neighbours -> tap_tab (temporarily
- *                 the count) and per-row extra-space demand -> extra_need [rows]
- * (exclusive scan of extra_need is done by of_exclusive_scan_i32)
+ * of_leaf_rank / of_compact_idx   per level: rank of every leaf among the leaves of its depth, and the
+ *                 index lists of leaf / non-empty nodes (row maps of GraphDownsample / GraphUpsample)
+ * of_graph_count  pass 1: need[row*7+dir] = words of tap_extra the slot needs (0 for <= 1 neighbour)
+ * of_exclusive_scan_i32 over `need`
  * of_graph_fill   pass 2: final tap_tab [rows, 7] (dir 6 = self loop, dual_octree.py:241-249) and
  *                 tap_extra; also node_type [rows] uint8 (:381-389) and batch_id [rows] int32 (:65-79)
  * ------------------------------------------------------------------------------------------ */

@@ -24,6 +24,7 @@
 // The one-hot node-type columns (modules.py:199-202) become one extra K block of per-slot
 // type fractions; the weights are re-laid once by of_pack_weight_tc.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace of {
 
@@ -154,6 +155,34 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// mean of n source rows (fp32 accumulate) -> one 16-byte bf16 chunk in shared memory.  Rare path
+// (coarse leaves next to subdivided cells), kept out of line to keep the hot loop small.
+__device__ __noinline__ void gather_mean_slow(uint32_t dst, const __nv_bfloat16* src, int64_t ld, const int32_t* e) {
+  const int n = e[0];
+  float sacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sacc[j] = 0.0f;
+  for (int k = 1; k <= n; ++k) {
+    float f[8];
+    bf16x8_to_f32(ldg_nc_v4(src + (int64_t)e[k] * ld), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sacc[j] += f[j];
+  }
+  const float dn = (float)n;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sacc[j] = sacc[j] / dn;
+  sts_v4(dst, f32_to_bf16x8(sacc));
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
@@ -179,6 +208,7 @@ struct TcParams {
   int cblocks;       // (c0+c1)/64
   int npad;          // N rounded up to 16 (rows per K block in the packed weight image)
   int m_tiles, n_tiles;
+  int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -206,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 
   if (warp == TC_EPI_WARPS && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, TC_PROD_WARPS / TC_GROUPS + 1);
+      mbar_init(bar_full + 8 * s, (TC_PROD_WARPS / TC_GROUPS) * 32 + 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -243,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c0);
         if (CH == 32) { OF_TMEM_LD32(taddr, acc); } else { OF_TMEM_LD16(taddr, acc); }
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (!row_ok || (p.debug & 4)) continue;
         const int nb = n0 + c0;
         float v[32];
 #pragma unroll
@@ -314,6 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
+            if (p.debug & 8) break;
             umma_bf16(d_tmem, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
                       (kb > 0 || k > 0) ? 1u : 0u);
           }
@@ -334,8 +365,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t b_addr = stage_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::B_BYTES);
-          bulk_g2s(b_addr, wp + ((int64_t)kb * p.npad + n0) * 128, Cfg::B_BYTES, bar_full + 8 * stage);
+          if (p.debug & 2) { mbar_arrive(bar_full + 8 * stage); }
+          else {
+            mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::B_BYTES);
+            bulk_g2s(b_addr, wp + ((int64_t)kb * p.npad + n0) * 128, Cfg::B_BYTES, bar_full + 8 * stage);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -353,61 +387,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(g.a0);
     const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(g.a1);
     const int32_t* __restrict__ tab = g.tap_tab;
-    uint32_t kbg = 0;                                               // running K-block index of this CTA
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // K blocks of this CTA in consumption order: kbg = tile_iter * num_kb + kb; this group owns kbg = grp (mod 4).
+    // The 16 table entries of the NEXT owned block are fetched before waiting for the current stage to be
+    // released, which takes the table latency off the stage turnaround.
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t kb_total = (uint32_t)my_tiles * (uint32_t)p.num_kb;
+    const int feat_kb = p.cblocks * taps;
+    auto fetch_taps = [&](uint32_t kk, int32_t* t) {
+      const int tile_iter = (int)(kk / (uint32_t)p.num_kb);
+      const int kb = (int)(kk - (uint32_t)tile_iter * (uint32_t)p.num_kb);
+      const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
       const int m0 = (tile / p.n_tiles) * TC_BM;
-      for (int kb = 0; kb < p.num_kb; ++kb, ++kbg) {
-        if ((int)(kbg % TC_GROUPS) != grp) continue;
+      if (kb >= feat_kb) return;
+      const int tap = kb % taps;
+      if (tab != nullptr) {
+        const uint32_t base = (uint32_t)(m0 + rbase) * (uint32_t)taps + (uint32_t)tap;     // < 2^31 (checked on host)
+#pragma unroll
+        for (int i = 0; i < TC_BM / 8; ++i) {
+          const int m = m0 + rbase + 8 * i;
+          t[i] = -1;
+          if (m < g.M) t[i] = __ldg(tab + (base + (uint32_t)(8 * i) * (uint32_t)taps));
+        }
+      } else if (g.in_rows != nullptr) {
+#pragma unroll
+        for (int i = 0; i < TC_BM / 8; ++i) {
+          const int m = m0 + rbase + 8 * i;
+          t[i] = -1;
+          if (m < g.M) t[i] = __ldg(g.in_rows + m);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < TC_BM / 8; ++i) {
+          const int m = m0 + rbase + 8 * i;
+          t[i] = m < g.M ? m : -1;
+        }
+      }
+    };
+    int32_t tnext[TC_BM / 8];
+    if ((uint32_t)grp < kb_total) fetch_taps((uint32_t)grp, tnext);
+    for (uint32_t kbg = (uint32_t)grp; kbg < kb_total; kbg += TC_GROUPS) {
+      {
+        const int tile_iter = (int)(kbg / (uint32_t)p.num_kb);
+        const int kb = (int)(kbg - (uint32_t)tile_iter * (uint32_t)p.num_kb);
+        const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
+        const int m0 = (tile / p.n_tiles) * TC_BM;
+        int32_t t[TC_BM / 8];
+#pragma unroll
+        for (int i = 0; i < TC_BM / 8; ++i) t[i] = tnext[i];
+        if (kbg + TC_GROUPS < kb_total) fetch_taps(kbg + TC_GROUPS, tnext);
         const uint32_t stage = kbg % Cfg::STAGES;
         const uint32_t phase = (kbg / Cfg::STAGES) & 1u;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
-        if (kb < p.cblocks * taps) {
+        if (p.debug & 1) {
+        } else if (kb < p.cblocks * taps) {
           const int cb = kb / taps, tap = kb - cb * taps;
           const int ch = cb * TC_BK;
           const __nv_bfloat16* src;
           int64_t ld;
           if (ch < g.c0) { src = a0 + ch; ld = g.lda0; } else { src = a1 + (ch - g.c0); ld = g.lda1; }
           src += q * 8;
+          if (p.debug & 16) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            int32_t t[8];
-            uint4 val[8];
+            for (int i = 0; i < TC_BM / 8; ++i) t[i] = 0;          // timing experiment: pure L1 hits
+          }
+          if (p.debug & 64) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int m = m0 + rbase + 8 * (half * 8 + i);
-              int32_t v = -1;
-              if (m < g.M) v = tab ? __ldg(tab + (int64_t)m * taps + tap) : (g.in_rows ? __ldg(g.in_rows + m) : m);
-              t[i] = v;
-            }
+            for (int i = 0; i < TC_BM / 8; ++i) if (t[i] < -1) t[i] = -1;   // timing experiment: drop multi-neighbour slots
+          }
+          // 2) ... then 16 asynchronous 16-byte global->shared copies back to back (no registers, no waiting);
+          //    a missing neighbour is a zero fill; the rare multi-neighbour slots are deferred
+          uint32_t slowmask = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              val[i] = make_uint4(0u, 0u, 0u, 0u);
-              if (t[i] >= 0) val[i] = ldg_nc_v4(src + (int64_t)t[i] * ld);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (t[i] < -1) {                                       // 4..16 finer neighbours: mean in fp32
-                const int32_t* e = g.tap_extra + (-(t[i] + 2));
-                const int n = e[0];
-                float sacc[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) sacc[j] = 0.0f;
-                for (int k = 1; k <= n; ++k) {
-                  float f[8];
-                  bf16x8_to_f32(ldg_nc_v4(src + (int64_t)e[k] * ld), f);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) sacc[j] += f[j];
-                }
-                const float dn = (float)n;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) sacc[j] = sacc[j] / dn;
-                val[i] = f32_to_bf16x8(sacc);
-              }
-              const int rr = rbase + 8 * (half * 8 + i);
-              sts_v4(a_addr + rr * 128 + ((q ^ (rr & 7)) << 4), val[i]);
+          for (int i = 0; i < TC_BM / 8; ++i) {
+            const int rr = rbase + 8 * i;
+            const uint32_t dst = a_addr + rr * 128 + ((q ^ (rr & 7)) << 4);
+            const bool one = t[i] >= 0;
+            const void* sp = one ? (const void*)(src + (int64_t)t[i] * ld) : (const void*)src;
+            if (t[i] >= -1) {
+              if (p.debug & 128) cp_async_16_ca(dst, sp, one ? 16u : 0u);
+              else cp_async_16(dst, sp, one ? 16u : 0u);
+            } else slowmask |= 1u << i;
+          }
+          bool slow = slowmask != 0;
+          if (slow) {
+#pragma unroll 1
+            for (int i = 0; i < TC_BM / 8; ++i) {
+              if (!((slowmask >> i) & 1u)) continue;
+              const int rr = rbase + 8 * i;
+              const int m = m0 + rr;
+              const int32_t tv = __ldg(tab + (int64_t)m * taps + tap);
+              gather_mean_slow(a_addr + rr * 128 + ((q ^ (rr & 7)) << 4), src, ld, g.tap_extra + (-(tv + 2)));
             }
           }
+          if (slow) fence_proxy_async_smem();
         } else {
           // node-type block: column tap*ntype + type holds (#neighbours of that type)/(#neighbours)
           // = mean of the one-hot columns the reference concatenates (modules.py:199-202).
@@ -440,10 +513,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
               }
             }
           }
+          fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core
         }
-        fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        // CUTLASS sm100 cp.async+UMMA protocol: one arrive that fires when this thread's cp.asyncs have
+        // landed (self-incrementing, not counted) + one ordinary release-arrive (counted)
+        cp_async_mbar_arrive(bar_full + 8 * stage);
+        mbar_arrive(bar_full + 8 * stage);
       }
     }
   }
@@ -553,6 +628,11 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
   if (a.M == 0) return OF_OK;
   TcParams p;
   p.g = a;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("OCTFUSION_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   p.cblocks = (a.c0 + a.c1) / 64;
   p.num_kb = p.cblocks * a.taps + (a.ntype > 0 ? 1 : 0);
   p.npad = (a.N + 15) / 16 * 16;
