@@ -84,6 +84,11 @@ typedef struct of_gemm_args {
   int32_t out_f32;                               /* 1: write fp32 regardless of dtype         */
   int32_t M, N;
   int32_t dtype;                                 /* activation dtype of a0/a1/resid/out       */
+  /* tcgen05 path only: slots with several neighbours read their pre-averaged row.  There tap_tab uses
+   * the ORDINAL encoding of of_graph_multi_index: v <= -2 -> row -(v+2) of a_multi (built per input tensor
+   * by of_gather_mean_rows); multi_types[ord] = per-type neighbour counts, 8 bits per type.            */
+  const void* a_multi; int64_t ld_multi;
+  const uint64_t* multi_types;
 } of_gemm_args;
 
 /* CUDA-core FFMA path: any shape, fp32-exact accumulation order-insensitive to 1e-6. */
@@ -201,6 +206,19 @@ int of_graph_count(const of_octree_levels* oct, int32_t D, int32_t* need, void* 
 int of_graph_fill(const of_octree_levels* oct, int32_t D, const int32_t* need_off,
                   int32_t* tap_tab, int32_t* tap_extra, uint8_t* node_type, int32_t* batch_id,
                   void* stream);
+/* Multi-neighbour slots (coarse leaf next to a subdivided cell: 4..16 finer neighbours, averaged by
+ * scatter_mean, utils/scatter.py:42-66).  of_graph_multi_flags marks them (flags[i] = tap_tab[i] <= -2);
+ * after an exclusive scan of the flags, of_graph_multi_index writes the ordinal-encoded table used by the
+ * tcgen05 path (v <= -2 -> -(ordinal+2)), multi_off[ord] = offset of the slot's record in tap_extra, and
+ * multi_types[ord] = packed per-type neighbour counts (8 bits per node type).
+ * of_gather_mean_rows: out[ord, :] = mean over the slot's neighbours of (a0|a1)[row, :]  (per input tensor). */
+int of_graph_multi_flags(const int32_t* tap_tab, int64_t slots, int32_t* flags, void* stream);
+int of_graph_multi_index(const int32_t* tap_tab, const int32_t* tap_extra, const uint8_t* node_type,
+                         int64_t slots, const int32_t* flag_scan, int32_t* tap_tab_ord, int32_t* multi_off,
+                         uint64_t* multi_types, void* stream);
+int of_gather_mean_rows(const void* a0, int64_t lda0, int32_t c0, const void* a1, int64_t lda1, int32_t c1,
+                        const int32_t* tap_extra, const int32_t* multi_off, int32_t count, int32_t dtype,
+                        void* out, int64_t ldo, void* stream);
 /* hist[v] += 1 for v = values[i] (caller zeroes hist) -- rows per sample for the norm count */
 int of_histogram_i32(const int32_t* values, int64_t n, int32_t bins, int32_t* hist, void* stream);
 /* reference-format edge list (edge_idx [2,E], edge_dir [E] int64, sorted by row*7+dir:

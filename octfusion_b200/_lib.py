@@ -34,6 +34,8 @@ class GemmArgs(C.Structure):
         ('out_f32', _i32),
         ('M', _i32), ('N', _i32),
         ('dtype', _i32),
+        ('a_multi', _vp), ('ld_multi', _i64),
+        ('multi_types', _vp),
     ]
 
 
@@ -73,6 +75,9 @@ _PROTOS = {
     'of_graph_count': (C.c_int, [C.POINTER(OctreeLevels), _i32, _vp, _vp]),
     'of_graph_fill': (C.c_int, [C.POINTER(OctreeLevels), _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'of_histogram_i32': (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    'of_graph_multi_flags': (C.c_int, [_vp, _i64, _vp, _vp]),
+    'of_graph_multi_index': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'of_gather_mean_rows': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     'of_graph_edge_count': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'of_graph_edges': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     'of_dense_tap_table': (C.c_int, [_i32, _i32, _i32, _vp, _vp]),

@@ -165,24 +165,6 @@ __device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, ui
 __device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-// mean of n source rows (fp32 accumulate) -> one 16-byte bf16 chunk in shared memory.  Rare path
-// (coarse leaves next to subdivided cells), kept out of line to keep the hot loop small.
-__device__ __noinline__ void gather_mean_slow(uint32_t dst, const __nv_bfloat16* src, int64_t ld, const int32_t* e) {
-  const int n = e[0];
-  float sacc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sacc[j] = 0.0f;
-  for (int k = 1; k <= n; ++k) {
-    float f[8];
-    bf16x8_to_f32(ldg_nc_v4(src + (int64_t)e[k] * ld), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sacc[j] += f[j];
-  }
-  const float dn = (float)n;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sacc[j] = sacc[j] / dn;
-  sts_v4(dst, f32_to_bf16x8(sacc));
-}
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
@@ -451,36 +433,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 #pragma unroll
             for (int i = 0; i < TC_BM / 8; ++i) t[i] = 0;          // timing experiment: pure L1 hits
           }
-          if (p.debug & 64) {
-#pragma unroll
-            for (int i = 0; i < TC_BM / 8; ++i) if (t[i] < -1) t[i] = -1;   // timing experiment: drop multi-neighbour slots
-          }
-          // 2) ... then 16 asynchronous 16-byte global->shared copies back to back (no registers, no waiting);
-          //    a missing neighbour is a zero fill; the rare multi-neighbour slots are deferred
-          uint32_t slowmask = 0;
+          // 16 asynchronous 16-byte global->shared copies back to back (no registers, no waiting):
+          // one neighbour -> its row; none -> zero fill; several -> the pre-averaged row of a_multi
+          const __nv_bfloat16* msrc = reinterpret_cast<const __nv_bfloat16*>(g.a_multi) + ch + q * 8;
 #pragma unroll
           for (int i = 0; i < TC_BM / 8; ++i) {
             const int rr = rbase + 8 * i;
             const uint32_t dst = a_addr + rr * 128 + ((q ^ (rr & 7)) << 4);
-            const bool one = t[i] >= 0;
-            const void* sp = one ? (const void*)(src + (int64_t)t[i] * ld) : (const void*)src;
-            if (t[i] >= -1) {
-              if (p.debug & 128) cp_async_16_ca(dst, sp, one ? 16u : 0u);
-              else cp_async_16(dst, sp, one ? 16u : 0u);
-            } else slowmask |= 1u << i;
+            const int32_t tv = t[i];
+            const void* sp = tv >= 0 ? (const void*)(src + (int64_t)tv * ld)
+                                     : (tv == -1 ? (const void*)src : (const void*)(msrc + (int64_t)(-(tv + 2)) * g.ld_multi));
+            if (p.debug & 128) cp_async_16_ca(dst, sp, tv == -1 ? 0u : 16u);
+            else cp_async_16(dst, sp, tv == -1 ? 0u : 16u);
           }
-          bool slow = slowmask != 0;
-          if (slow) {
-#pragma unroll 1
-            for (int i = 0; i < TC_BM / 8; ++i) {
-              if (!((slowmask >> i) & 1u)) continue;
-              const int rr = rbase + 8 * i;
-              const int m = m0 + rr;
-              const int32_t tv = __ldg(tab + (int64_t)m * taps + tap);
-              gather_mean_slow(a_addr + rr * 128 + ((q ^ (rr & 7)) << 4), src, ld, g.tap_extra + (-(tv + 2)));
-            }
-          }
-          if (slow) fence_proxy_async_smem();
         } else {
           // node-type block: column tap*ntype + type holds (#neighbours of that type)/(#neighbours)
           // = mean of the one-hot columns the reference concatenates (modules.py:199-202).
@@ -495,14 +460,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
             for (int tap = 0; tap < taps; ++tap) {
               const int32_t tv = tab ? __ldg(tab + (int64_t)m * taps + tap) : m;
               if (tv == -1) continue;
-              unsigned long long packed = 0ull;
+              unsigned long long packed;
               int n = 1;
               if (tv >= 0) {
                 packed = 1ull << (8 * g.node_type[tv]);
               } else {
-                const int32_t* e = g.tap_extra + (-(tv + 2));
-                n = e[0];
-                for (int k = 1; k <= n; ++k) packed += 1ull << (8 * g.node_type[e[k]]);
+                packed = g.multi_types[-(tv + 2)];           // per-type neighbour counts of the slot
+                n = 0;
+                for (int ty = 0; ty < 8; ++ty) n += (int)((packed >> (8 * ty)) & 255ull);
               }
               for (int ty = 0; ty < g.ntype && ty < 8; ++ty) {
                 const int c = (int)((packed >> (8 * ty)) & 255ull);

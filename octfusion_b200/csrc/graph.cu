@@ -321,9 +321,125 @@ __global__ void edge_fill_kernel(const int32_t* __restrict__ tab, const int32_t*
   for (int j = 1; j <= n; ++j, ++o) { er[o] = row; ec[o] = e[j]; ed[o] = dir; }
 }
 
+__global__ void multi_flags_kernel(const int32_t* __restrict__ tab, int64_t slots, int32_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < slots) flags[i] = tab[i] <= -2 ? 1 : 0;
+}
+
+__global__ void multi_index_kernel(const int32_t* __restrict__ tab, const int32_t* __restrict__ extra,
+                                   const uint8_t* __restrict__ node_type, int64_t slots,
+                                   const int32_t* __restrict__ scan, int32_t* __restrict__ tab_ord,
+                                   int32_t* __restrict__ multi_off, unsigned long long* __restrict__ multi_types) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= slots) return;
+  const int32_t v = tab[i];
+  if (v > -2) { tab_ord[i] = v; return; }
+  const int32_t ord = scan[i];
+  const int32_t o = -(v + 2);
+  tab_ord[i] = -(ord + 2);
+  multi_off[ord] = o;
+  const int n = extra[o];
+  unsigned long long packed = 0ull;
+  for (int k = 1; k <= n; ++k) packed += 1ull << (8 * (node_type ? node_type[extra[o + k]] : 0));
+  multi_types[ord] = packed;
+}
+
+// one thread per (slot, 16-byte chunk): mean over the slot's neighbours, fp32 accumulate
+template <typename T, int V>
+__global__ void gather_mean_rows_kernel(const T* __restrict__ a0, int64_t lda0, int c0, const T* __restrict__ a1,
+                                        int64_t lda1, int c1, const int32_t* __restrict__ extra,
+                                        const int32_t* __restrict__ multi_off, int count, T* __restrict__ out,
+                                        int64_t ldo) {
+  const int cpr = (c0 + c1) / V;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)count * cpr) return;
+  const int ord = (int)(idx / cpr);
+  const int c = (int)(idx - (int64_t)ord * cpr) * V;
+  const int32_t* e = extra + multi_off[ord];
+  const int n = e[0];
+  const T* base = c < c0 ? a0 + c : a1 + (c - c0);
+  const int64_t ld = c < c0 ? lda0 : lda1;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+  for (int k = 1; k <= n; ++k) {
+    const T* src = base + (int64_t)e[k] * ld;
+    if (V == 8) {
+      float f[8];
+      bf16x8_to_f32(*reinterpret_cast<const uint4*>(src), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j % V] += f[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += Elem<T>::ld(src + j);
+    }
+  }
+  const float dn = (float)n;
+  T* o = out + (int64_t)ord * ldo + c;
+  if (V == 8) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = acc[j % V] / dn;
+    *reinterpret_cast<uint4*>(o) = f32_to_bf16x8(f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < V; ++j) Elem<T>::st(o + j, acc[j] / dn);
+  }
+}
+
 }  // namespace of
 
 using namespace of;
+
+extern "C" int of_graph_multi_flags(const int32_t* tap_tab, int64_t slots, int32_t* flags, void* stream) {
+  OF_REQUIRE(tap_tab && flags && slots >= 0, "of_graph_multi_flags: bad arguments");
+  if (slots == 0) return OF_OK;
+  multi_flags_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tap_tab, slots,
+                                                                                                        flags);
+  OF_LAUNCH_CHECK("of_graph_multi_flags");
+  return OF_OK;
+}
+
+extern "C" int of_graph_multi_index(const int32_t* tap_tab, const int32_t* tap_extra, const uint8_t* node_type,
+                                    int64_t slots, const int32_t* flag_scan, int32_t* tap_tab_ord, int32_t* multi_off,
+                                    uint64_t* multi_types, void* stream) {
+  OF_REQUIRE(tap_tab && tap_extra && flag_scan && tap_tab_ord && multi_off && multi_types && slots >= 0,
+             "of_graph_multi_index: bad arguments");
+  if (slots == 0) return OF_OK;
+  multi_index_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tap_tab, tap_extra, node_type, slots, flag_scan, tap_tab_ord, multi_off,
+      reinterpret_cast<unsigned long long*>(multi_types));
+  OF_LAUNCH_CHECK("of_graph_multi_index");
+  return OF_OK;
+}
+
+extern "C" int of_gather_mean_rows(const void* a0, int64_t lda0, int32_t c0, const void* a1, int64_t lda1, int32_t c1,
+                                   const int32_t* tap_extra, const int32_t* multi_off, int32_t count, int32_t dtype,
+                                   void* out, int64_t ldo, void* stream) {
+  OF_REQUIRE(a0 && c0 > 0 && ((a1 == nullptr) == (c1 == 0)) && tap_extra && multi_off && out && count >= 0,
+             "of_gather_mean_rows: bad arguments");
+  OF_REQUIRE(dtype == OF_F32 || dtype == OF_BF16, "of_gather_mean_rows: bad dtype");
+  if (count == 0) return OF_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int C = c0 + c1;
+  if (dtype == OF_BF16 && c0 % 8 == 0 && c1 % 8 == 0 && lda0 % 8 == 0 && lda1 % 8 == 0 && ldo % 8 == 0) {
+    const int64_t n = (int64_t)count * (C / 8);
+    gather_mean_rows_kernel<__nv_bfloat16, 8><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)a0, lda0, c0, (const __nv_bfloat16*)a1, lda1, c1, tap_extra, multi_off, count,
+        (__nv_bfloat16*)out, ldo);
+  } else if (dtype == OF_BF16) {
+    const int64_t n = (int64_t)count * C;
+    gather_mean_rows_kernel<__nv_bfloat16, 1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)a0, lda0, c0, (const __nv_bfloat16*)a1, lda1, c1, tap_extra, multi_off, count,
+        (__nv_bfloat16*)out, ldo);
+  } else {
+    const int64_t n = (int64_t)count * C;
+    gather_mean_rows_kernel<float, 1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        (const float*)a0, lda0, c0, (const float*)a1, lda1, c1, tap_extra, multi_off, count, (float*)out, ldo);
+  }
+  OF_LAUNCH_CHECK("of_gather_mean_rows");
+  return OF_OK;
+}
 
 extern "C" int64_t of_scan_scratch_bytes(int64_t n) {
   return ((n + SCAN_B - 1) / SCAN_B + 1) * (int64_t)sizeof(int32_t);

@@ -109,7 +109,7 @@ class DualOctree:
             check(lib.of_histogram_i32(ptr(bid), rows, self.batch_size, ptr(hist), stream()), 'of_histogram_i32')
             p = GraphPlan()
             p.depth, p.rows = D, rows
-            p.tap = ops.TapTable(tab, extra, N_DIR)
+            p.tap = ops.TapTable(tab, extra, N_DIR).index_multi(ntype)
             p.node_type, p.batch_id, p.rows_of_sample = ntype, bid, hist
             p.leaf_base = int(self.lnum[fd:D].sum())          # rows of leaves coarser than D
             self.plan[D] = p

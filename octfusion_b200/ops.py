@@ -28,13 +28,34 @@ def set_force_simt(flag: bool):
 
 
 class TapTable:
-    """Neighbour table of the tap-gather GEMM (see include/octfusion_b200.h)."""
-    __slots__ = ('tab', 'extra', 'taps', 'rows')
+    """Neighbour table of the tap-gather GEMM (see include/octfusion_b200.h).
+    tab/extra: record encoding (CUDA-core path).  tab_ord/multi_off/multi_types: ordinal encoding of the
+    multi-neighbour slots for the tcgen05 path (of_graph_multi_index); n_multi = number of such slots."""
+    __slots__ = ('tab', 'extra', 'taps', 'rows', 'tab_ord', 'multi_off', 'multi_types', 'n_multi')
 
     def __init__(self, tab: torch.Tensor, extra, taps: int):
         assert tab.dtype == torch.int32 and tab.is_contiguous()
         self.tab, self.extra, self.taps = tab, extra, taps
         self.rows = tab.numel() // taps
+        self.tab_ord, self.multi_off, self.multi_types, self.n_multi = tab, None, None, 0
+
+    def index_multi(self, node_type=None):
+        """build the ordinal-encoded table (once per graph)."""
+        slots = self.tab.numel()
+        dev = self.tab.device
+        flags = torch.empty(slots, dtype=torch.int32, device=dev)
+        check(lib.of_graph_multi_flags(ptr(self.tab), slots, ptr(flags), stream()), 'of_graph_multi_flags')
+        scan = exclusive_scan_i32(flags)
+        self.n_multi = int(scan[-1].item())
+        if self.n_multi == 0:
+            return self
+        self.tab_ord = torch.empty_like(self.tab)
+        self.multi_off = torch.empty(self.n_multi, dtype=torch.int32, device=dev)
+        self.multi_types = torch.empty(self.n_multi, dtype=torch.int64, device=dev)
+        check(lib.of_graph_multi_index(ptr(self.tab), ptr(self.extra), ptr(node_type) if node_type is not None else None,
+                                       slots, ptr(scan), ptr(self.tab_ord), ptr(self.multi_off),
+                                       ptr(self.multi_types), stream()), 'of_graph_multi_index')
+        return self
 
 
 class PreparedWeight:
@@ -122,7 +143,18 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g = GemmArgs()
     g.a0, g.lda0, g.c0 = a0.data_ptr(), a0.stride(0), c0
     g.a1, g.lda1, g.c1 = (a1.data_ptr(), a1.stride(0), c1) if a1 is not None else (None, 0, 0)
-    g.tap_tab = tap.tab.data_ptr() if tap is not None else None
+    g.a_multi, g.ld_multi, g.multi_types = None, 0, None
+    if tap is not None and use_tc:
+        g.tap_tab = tap.tab_ord.data_ptr()
+        if tap.n_multi > 0:
+            # slots with several (4..16) finer neighbours: their mean rows are built once per input tensor
+            aux = torch.empty((tap.n_multi, c0 + c1), dtype=act_dtype, device=a0.device)
+            check(lib.of_gather_mean_rows(a0.data_ptr(), a0.stride(0), c0, a1.data_ptr() if a1 is not None else None,
+                                          a1.stride(0) if a1 is not None else 0, c1, ptr(tap.extra), ptr(tap.multi_off),
+                                          tap.n_multi, dt(a0), ptr(aux), aux.stride(0), stream()), 'of_gather_mean_rows')
+            g.a_multi, g.ld_multi, g.multi_types = aux.data_ptr(), aux.stride(0), tap.multi_types.data_ptr()
+    else:
+        g.tap_tab = tap.tab.data_ptr() if tap is not None else None
     g.tap_extra = tap.extra.data_ptr() if (tap is not None and tap.extra is not None) else None
     g.in_rows = in_rows.data_ptr() if in_rows is not None else None
     g.taps = taps
