@@ -143,6 +143,11 @@ int of_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int
 /* ------------------------------------------------------------------------------------------
  * Small per-step pieces
  * ------------------------------------------------------------------------------------------ */
+/* out[b,:] = act(x[b,:]) . W^T + bias for a few rows (B <= a few dozen): the nn.Linear layers of the
+ * timestep-embedding path (graph_unet_hr.py:107-111, modules.py:709-715 emb_layers, :479-482 time_mlp).
+ * w_nk is the nn.Linear weight in its native [N, K] layout; a_silu applies SiLU to x on load. */
+int of_linear_small(const float* x, int64_t ldx, const float* w_nk, const float* bias, int32_t B, int32_t K,
+                    int32_t N, int32_t a_silu, float* out, int64_t ldo, void* stream);
 /* timestep_embedding  diffusion_networks/ldm_diffusion_util.py:171-191  ->  out [B, dim] fp32 */
 int of_timestep_embedding(const float* t, int32_t batch, int32_t dim, float max_period, float* out,
                           void* stream);

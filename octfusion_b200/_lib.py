@@ -62,6 +62,7 @@ _PROTOS = {
     'of_gn_finalize': (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp]),
     'of_gn_apply': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     'of_attention': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'of_linear_small': (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     'of_timestep_embedding': (C.c_int, [_vp, _i32, _i32, _f32, _vp, _vp]),
     'of_learned_sinusoidal': (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     'of_embedding_add': (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),

@@ -43,6 +43,13 @@ template <> struct Elem<__nv_bfloat16> {
 };
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// one MUFU op instead of two: x*sigmoid(x) = 0.5x(1 + tanh(x/2)); tanh.approx is good to ~2^-11, i.e. below
+// the bf16 rounding of the stored result (used for bf16 outputs only)
+__device__ __forceinline__ float silu_fast(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+  return 0.5f * v * (1.0f + t);
+}
 
 // 8 bf16 <-> 8 floats through one 16-byte register quad
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& q, float* f) {

@@ -175,6 +175,49 @@ __global__ void dense_tap_table_kernel(int mode, int out_bits, int batch, int32_
   tab[i] = v;
 }
 
+// out[b, n] = sum_k act(x[b, k]) * W[n, k] + bias[n] for a handful of rows (the [B, 512] timestep-embedding
+// MLPs: nn.Linear layers of time_embed / emb_layers / time_mlp, reference graph_unet_hr.py:107-111,
+// modules.py:709-715,479-482).  One warp per output column; x is staged in shared memory; W is read once,
+// coalesced along k, in its native nn.Linear [N, K] layout.
+__global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, int64_t ldx,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           int B, int K, int N, int a_silu, float* __restrict__ out,
+                                                           int64_t ldo) {
+  extern __shared__ float xs[];                     // [min(B,32)][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int nb = min(32, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * K; i += blockDim.x) {
+      const int b = i / K, k = i - b * K;
+      float v = x[(int64_t)(b0 + b) * ldx + k];
+      xs[i] = a_silu ? silu_f(v) : v;
+    }
+    __syncthreads();
+    if (n >= N) continue;
+    float acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = 0.0f;
+    const float* wr = w + (int64_t)n * K;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = wr[k];
+#pragma unroll
+      for (int b = 0; b < 32; ++b)
+        if (b < nb) acc[b] = fmaf(xs[b * K + k], wv, acc[b]);
+    }
+    float mine = 0.0f;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      float v = acc[b];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == b) mine = v;
+    }
+    if (lane < nb) out[(int64_t)(b0 + lane) * ldo + n] = mine + (bias ? bias[n] : 0.0f);
+  }
+}
+
 static inline int grid_for(int64_t n, int block = 256, int cap_mult = 32) {
   int64_t want = (n + block - 1) / block;
   int64_t cap = (int64_t)num_sms() * cap_mult;
@@ -193,6 +236,22 @@ extern "C" int of_repack_weight(const float* src, int64_t s_tap, int64_t s_c, in
   repack_weight_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, s_tap, s_c, s_n,
                                                                                            taps, c, N, dst);
   OF_LAUNCH_CHECK("of_repack_weight");
+  return OF_OK;
+}
+
+extern "C" int of_linear_small(const float* x, int64_t ldx, const float* w_nk, const float* bias, int32_t B, int32_t K,
+                               int32_t N, int32_t a_silu, float* out, int64_t ldo, void* stream) {
+  OF_REQUIRE(x && w_nk && out && B > 0 && K > 0 && N > 0, "of_linear_small: bad arguments");
+  const size_t smem = (size_t)(B < 32 ? B : 32) * K * sizeof(float);
+  OF_REQUIRE(smem <= 200 * 1024, "of_linear_small: K=%d too large for the shared staging buffer", K);
+  static size_t cfg = 48 * 1024;
+  if (smem > cfg) {
+    cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cfg = 200 * 1024;
+  }
+  linear_small_kernel<<<(N + 7) / 8, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, w_nk, bias, B, K, N,
+                                                                                          a_silu, out, ldo);
+  OF_LAUNCH_CHECK("of_linear_small");
   return OF_OK;
 }
 

@@ -140,26 +140,40 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, const int32_
   shift[i] = (float)((double)beta[c] - m * rstd * ga);
 }
 
+template <typename T> struct FastAct;
+template <> struct FastAct<float> { static __device__ __forceinline__ float silu(float v) { return silu_f(v); } };
+template <> struct FastAct<__nv_bfloat16> { static __device__ __forceinline__ float silu(float v) { return silu_fast(v); } };
+
+// Each thread owns one channel vector and walks down the rows of its CTA's 256-row chunk; the per-(sample,
+// channel) scale/shift pair stays in registers until the sample id changes.
 template <typename T, int V>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int act, T* y,
                                                        int64_t ldy) {
   const int C = s.c0 + s.c1;
   const int tpr = C / V;
-  const int64_t total = s.rows * tpr;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = idx / tpr;
-    const int cv = (int)(idx - r * tpr) * V;
+  const int rp = blockDim.x / tpr;
+  if ((int)threadIdx.x >= rp * tpr) return;
+  const int cv = (threadIdx.x % tpr) * V;
+  const int64_t r0 = (int64_t)blockIdx.x * GN_ROWS_PER_CTA;
+  const int64_t r1 = min(r0 + (int64_t)GN_ROWS_PER_CTA, s.rows);
+  float sc[V], sh[V];
+  int cur_b = -1;
+  for (int64_t r = r0 + threadIdx.x / tpr; r < r1; r += rp) {
     const int b = s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample);
+    if (b != cur_b) {
+      cur_b = b;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { sc[i] = scale[(int64_t)b * C + cv + i]; sh[i] = shift[(int64_t)b * C + cv + i]; }
+    }
     float f[V];
     load_vec<T, V>(src_ptr<T, V>(s, r, cv), f);
-    const float* sc = scale + (int64_t)b * C + cv;
-    const float* sh = shift + (int64_t)b * C + cv;
+    if (act) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float v = fmaf(f[i], sc[i], sh[i]);
-      f[i] = act ? silu_f(v) : v;
+      for (int i = 0; i < V; ++i) f[i] = FastAct<T>::silu(fmaf(f[i], sc[i], sh[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
     }
     store_vec<T, V>(y + r * ldy + cv, f);
   }
@@ -245,12 +259,10 @@ extern "C" int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* 
   if (rows == 0) return OF_OK;
   const int C = c0 + c1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int sms = num_sms();
 #define OF_GN_APPLY_LAUNCH(T, V)                                                              \
   do {                                                                                        \
-    int64_t total = rows * (C / V);                                                           \
-    int64_t want = (total + 255) / 256;                                                       \
-    int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);                    \
+    OF_REQUIRE(C / V <= 256, "of_gn_apply: C=%d too wide", C);                                \
+    const int grid = (int)((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA);                   \
     gn_apply_kernel<T, V><<<grid, 256, 0, st>>>(s, scale, shift, act, reinterpret_cast<T*>(y), ldy); \
   } while (0)
   if (dtype == OF_F32) {

@@ -20,7 +20,7 @@ class _Linear(nn.Linear):
         return self._pw.refresh(self.weight, 'linear')
 
     def run(self, x, a_silu=False):
-        return ops.gather_gemm(x, self.prepared(), bias=self.bias, a_silu=a_silu)
+        return ops.linear_small(x, self.weight, self.bias, a_silu=a_silu)
 
 
 class UNet3DModel(nn.Module):

@@ -60,7 +60,28 @@ class GraphConv(nn.Module):
     def prepared(self):
         return self._pw.refresh(self.weights, 'canon')
 
+    def prepared_padded(self, cpad=64):
+        """weights re-laid for an input zero-padded to `cpad` channels (tcgen05 path needs C % 64 == 0; the
+        3- or 8-channel latent of the first conv is padded instead of falling back to the CUDA cores)."""
+        key = (self.weights.data_ptr(), self.weights._version)
+        if getattr(self, '_pw_pad_key', None) != key:
+            cin, nt, k = self.in_channels, self.node_channel, self.n_edge_type
+            w = self.weights.detach().float().view(k, cin + nt, self.out_channels)
+            wp = torch.zeros((k, cpad + nt, self.out_channels), dtype=torch.float32, device=w.device)
+            wp[:, :cin] = w[:, :cin]
+            wp[:, cpad:] = w[:, cin:]
+            self._pw_pad = PreparedWeight(k, cpad, nt, self.out_channels)
+            self._pw_pad.refresh(wp.view(-1, self.out_channels), 'canon')
+            self._pw_pad_src = wp
+            self._pw_pad_key = key
+        return self._pw_pad
+
     def run(self, x0, plan, x1=None, **epi):
+        if x1 is None and x0.dtype == torch.bfloat16 and self.in_channels % 64 != 0 and self.in_channels < 64:
+            xp = torch.zeros((x0.shape[0], 64), dtype=x0.dtype, device=x0.device)
+            ops.copy_rows(x0, xp, x0.shape[0], self.in_channels)
+            return ops.gather_gemm(xp, self.prepared_padded(64), tap=plan.tap, node_type=plan.node_type,
+                                   bias=self.bias if self.use_bias else None, **epi)
         return ops.gather_gemm(x0, self.prepared(), a1=x1, tap=plan.tap, node_type=plan.node_type,
                                bias=self.bias if self.use_bias else None, **epi)
 
@@ -249,7 +270,7 @@ class GraphResBlockEmbed(TimestepBlock):
         """x = (x0 | x1) virtual concat; emb fp32 [B, emb_channels]."""
         h = self.block1_norm.run(x0, plan, batch_size, x1=x1, act=True)
         lin = self.emb_layers[1]
-        e = ops.gather_gemm(emb, self._pw_emb.refresh(lin.weight, 'linear'), a_silu=True, bias=lin.bias)
+        e = ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
         h = self.conv1.run(h, plan, row_add=e, row_add_idx=plan.batch_id)
         h = self.block2_norm.run(h, plan, batch_size, act=True)
         if isinstance(self.skip_connection, Conv1x1):
@@ -442,7 +463,7 @@ class ResnetBlock(nn.Module):
         tap = tables.conv(res_log2)
         h = self.block1[0].run(x0, b, v, x1=x1, act=True)
         lin = self.time_mlp[1]
-        t = ops.gather_gemm(emb, self._pw_t.refresh(lin.weight, 'linear'), a_silu=True, bias=lin.bias)
+        t = ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
         h = self.block1[2].run(h, tap, row_add=t, row_add_idx=tables.sample_id(res_log2))
         h = self.block2[0].run(h, b, v, act=True)
         if isinstance(self.res_conv, nn.Identity):

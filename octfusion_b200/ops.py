@@ -21,6 +21,22 @@ def set_profile(sink):
     _PROFILE = sink
 
 
+_TRACE = None          # debug: list receiving (op, shape, checksum) for every op output
+
+
+def set_trace(sink):
+    global _TRACE
+    _TRACE = sink
+
+
+_TRACE_KEEP = False
+
+
+def _trace(op, t):
+    if _TRACE is not None:
+        _TRACE.append((op, tuple(t.shape), float(t.float().abs().sum()), t.clone() if _TRACE_KEEP else None))
+
+
 def set_force_simt(flag: bool):
     """Debug switch: route every GEMM through the CUDA-core kernel."""
     global _FORCE_SIMT
@@ -192,6 +208,20 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
                          bytes=float(m * (c0 + c1) * es + m * n * (4 if g.out_f32 else es) + nnz * 4 + k * n * es
                                      + (m * n * es if resid is not None else 0)),
                          start=e0, end=e1))
+    _trace('gemm_tc' if use_tc else 'gemm_simt', out)
+    return out
+
+
+def linear_small(x, weight, bias=None, a_silu=False):
+    """out = act(x) @ weight.T + bias for a few rows of fp32 (timestep-embedding MLPs); weight is [N, K]."""
+    _lib.require_cuda(x, weight, bias)
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and weight.dtype == torch.float32 and weight.is_contiguous()
+    b, k = x.shape
+    n = weight.shape[0]
+    out = torch.empty((b, n), dtype=torch.float32, device=x.device)
+    check(lib.of_linear_small(ptr(x), x.stride(0), ptr(weight), ptr(bias) if bias is not None else None, b, k, n,
+                              1 if a_silu else 0, ptr(out), out.stride(0), stream()), 'of_linear_small')
+    _trace('linear_small', out)
     return out
 
 
@@ -218,6 +248,7 @@ def group_norm(x0, gamma, beta, groups: int, batch: int, *, x1=None, sample_id=N
         out = torch.empty((rows, c), dtype=x0.dtype, device=dev)
     check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, ptr(scale),
                           ptr(shift), 1 if act else 0, dt(x0), ptr(out), out.stride(0), stream()), 'of_gn_apply')
+    _trace('group_norm', out)
     return out
 
 
@@ -229,6 +260,7 @@ def attention(qkv, batch: int, tokens: int, heads: int, out=None):
         out = torch.empty((batch * tokens, c), dtype=qkv.dtype, device=qkv.device)
     check(lib.of_attention(ptr(qkv), qkv.stride(0), ptr(out), out.stride(0), batch, tokens, heads, ch, dt(qkv),
                            stream()), 'of_attention')
+    _trace('attention', out)
     return out
 
 

@@ -82,14 +82,19 @@ def test_group_norm_statistics_full_size(doc):
 
 
 def test_sampler_is_reproducible_full_size(doc):
+    """Two runs with the same seed.  Convolutions, attention and resampling are bit-deterministic
+    (tools/determinism_check.py); the norm statistics use floating-point atomics, so scale/shift can move by
+    one ulp between runs.  In fp32 that stays at the 1e-5 level.  In bf16 any such perturbation is amplified
+    by the rounding of every layer output until it reaches the bf16 noise floor of this network (~1.5e-2
+    relative L2, the same size as the bf16-vs-fp32 parity error) -- a race would show up as O(1)."""
     from octfusion_b200 import graph_unet_union
     from octfusion_b200.sampler import sample_loop
     from tests.util import UNCOND
     import bench
     net = bench.randomise_(graph_unet_union.UNet3DModel('hr', **UNCOND), 0).to(DEV).eval()
-    a = sample_loop(net.unet_hr, net.unet_lr, doc, ddim_steps=3, seed=5)
-    b = sample_loop(net.unet_hr, net.unet_lr, doc, ddim_steps=3, seed=5)
-    assert torch.isfinite(a).all() and float(a.abs().max()) > 0
-    # the norm statistics are accumulated with floating-point atomics (order varies run to run), so two
-    # runs agree to rounding, not bit for bit; a race would show up as O(1) differences
-    assert float((a - b).norm() / a.norm()) < 5e-3, 'two runs with the same seed differ (race?)'
+    for dtype, tol in ((torch.float32, 1e-3), (torch.bfloat16, 4e-2)):
+        a = sample_loop(net.unet_hr, net.unet_lr, doc, ddim_steps=2, seed=5, act_dtype=dtype)
+        b = sample_loop(net.unet_hr, net.unet_lr, doc, ddim_steps=2, seed=5, act_dtype=dtype)
+        assert torch.isfinite(a).all() and float(a.abs().max()) > 0
+        d = float((a - b).norm() / a.norm())
+        assert d < tol, (str(dtype), d)

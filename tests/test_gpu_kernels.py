@@ -243,3 +243,18 @@ def test_embeddings_and_ddim():
     ops.ddim_eps_update(xd, eps.to(DEV), ls.to(DEV), lsn.to(DEV), xa)
     assert relerr(xd.cpu(), ref) < 1e-5
     assert relerr(xa.float().cpu(), ref) < 8e-3
+
+
+@pytest.mark.parametrize('b,k,n', [(32, 512, 512), (2, 128, 512), (5, 65, 256), (40, 256, 64)])
+def test_linear_small(b, k, n):
+    from octfusion_b200 import ops
+    x, w, bias = _rand((b, k), 1), _rand((n, k), 2, 1 / math.sqrt(k)), _rand((n,), 3)
+    y = ops.linear_small(x.to(DEV), w.to(DEV), bias.to(DEV), a_silu=True).cpu()
+    assert relerr(y, F.linear(R.silu(x), w, bias)) < 1e-5
+
+
+def test_graphconv_small_channel_input_padded_to_tc():
+    """the 3- / 8-channel latent of the first conv is zero-padded to 64 channels for the tcgen05 path."""
+    for cin in (3, 8):
+        y, ref32, refbf = _graphconv_case(2, 6, cin, 128, 5, torch.bfloat16)
+        assert relerr(y, refbf) < 8e-3 and relerr(y, ref32) < 2e-2
