@@ -32,8 +32,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
 constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS + 1) * 32;   // 480 (last warp: L2 prefetcher)
-constexpr int TC_PF_DIST = 2;               // tiles the L2 prefetcher runs ahead of the MMA
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;   // 448
 constexpr int TC_MAX_TAPS = 27;
 constexpr int TC_GROUPS = 4;                // producer groups of 2 warps
 
@@ -212,7 +211,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAP_BYTES + 16 * Cfg::STAGES + 32);
 
-  volatile int* progress_gen = reinterpret_cast<volatile int*>(const_cast<uint32_t*>(tmem_slot_gen)) + 1;   // MMA tile counter
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const of_gemm_args& g = p.g;
   const int taps = g.taps;
@@ -227,7 +225,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS * 32);
     }
-    *progress_gen = 0;
     fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -337,7 +334,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(bar_tfull + 8 * as);                 // accumulator complete -> epilogue
-        *progress_gen = it + 1;
       }
     }
   } else if (warp == TC_EPI_WARPS + 1) {
@@ -358,52 +354,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-      }
-    }
-  } else if (warp == TC_EPI_WARPS + 2 + TC_PROD_WARPS) {
-    // =========================== L2 prefetcher ===========================
-    // Walks the tap table TC_PF_DIST tiles ahead of the MMA and touches every source line of that tile with
-    // prefetch.global.L2, so the cp.async gathers find their rows in L2 instead of paying the DRAM latency
-    // inside the smem ring (the ring holds only 4-5 K blocks; its turnaround time is what bounds the kernel).
-    if (!(p.debug & 256) && g.tap_tab != nullptr) {
-      const int32_t* __restrict__ tab = g.tap_tab;
-      const char* b0 = reinterpret_cast<const char*>(g.a0);
-      const char* b1 = reinterpret_cast<const char*>(g.a1);
-      const char* bm = reinterpret_cast<const char*>(g.a_multi);
-      const int lines0 = g.c0 / 64, lines1 = g.c1 / 64;
-      const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      auto prefetch_tile = [&](int it) {
-        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-        if (tile % p.n_tiles != 0 && it > 0) return;            // same rows as the previous n tile
-        const int m0 = (tile / p.n_tiles) * TC_BM;
-        for (int rr = lane; rr < TC_BM; rr += 32) {
-          const int m = m0 + rr;
-          if (m >= g.M) break;
-          for (int tap = 0; tap < taps; ++tap) {
-            const int32_t tv = __ldg(tab + (int64_t)m * taps + tap);
-            if (tv >= 0) {
-              const char* r0 = b0 + (int64_t)tv * g.lda0 * 2;
-              for (int l = 0; l < lines0; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + l * 128));
-              if (lines1) {
-                const char* r1 = b1 + (int64_t)tv * g.lda1 * 2;
-                for (int l = 0; l < lines1; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + l * 128));
-              }
-            } else if (tv < -1 && bm != nullptr) {
-              const char* rm = bm + (int64_t)(-(tv + 2)) * g.ld_multi * 2;
-              for (int l = 0; l < lines0 + lines1; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(rm + l * 128));
-            }
-          }
-        }
-      };
-      for (int it = 1; it <= TC_PF_DIST && it < my_tiles; ++it) prefetch_tile(it);
-      for (int it = 0; it + TC_PF_DIST + 1 < my_tiles; ++it) {
-        // pace on the MMA issuer's tile counter (a plain shared word: no mbarrier phase to alias)
-        const long long t0 = clock64();
-        while (*progress_gen <= it) {
-          __nanosleep(256);
-          if (clock64() - t0 > 4000000000ll) break;             // never hang the kernel for a prefetch
-        }
-        prefetch_tile(it + TC_PF_DIST + 1);
       }
     }
   } else {
