@@ -13,17 +13,18 @@ namespace of {
 
 constexpr int ATT_WARPS = 8;
 constexpr int ATT_QTILE = 128;
+constexpr int ATT_QB = 4;                 // queries processed together by one warp (register blocking)
 
 template <typename T>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __restrict__ qkv, int64_t ld_qkv,
                                                                    T* __restrict__ out, int64_t ld_out, int tokens,
                                                                    int heads, int ch) {
-  extern __shared__ float sm[];
-  const int kst = ch + 1;                               // padded row stride: conflict-free column reads
-  float* Ks = sm;                                       // [T][ch+1]
-  float* Vs = Ks + (size_t)tokens * kst;                // [T][ch+1]
-  float* Ps = Vs + (size_t)tokens * kst;                // [warps][T]
-  float* Qs = Ps + (size_t)ATT_WARPS * tokens;          // [warps][ch]
+  extern __shared__ __align__(16) float sm[];
+  const int kst = ch + 4;                               // 16-byte aligned rows, conflict-free float4 column reads
+  float* Ks = sm;                                       // [T][ch+4]
+  float* Vs = Ks + (size_t)tokens * kst;                // [T][ch+4]
+  float* Ps = Vs + (size_t)tokens * kst;                // [warps][T][QB]
+  float* Qs = Ps + (size_t)ATT_WARPS * tokens * ATT_QB; // [warps][QB][ch]
   const int bh = blockIdx.x;
   const int b = bh / heads, h = bh - b * heads;
   const int64_t row0 = (int64_t)b * tokens;
@@ -36,39 +37,68 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* P = Ps + (size_t)warp * tokens;
-  float* Q = Qs + (size_t)warp * ch;
+  float* P = Ps + (size_t)warp * tokens * ATT_QB;       // P[s][q]
+  float* Q = Qs + (size_t)warp * ATT_QB * ch;           // Q[q][c]
   const float scale = rsqrtf((float)ch);                // (ch^-1/4)^2, modules.py:542-545
   const int q_end = min(tokens, (int)(blockIdx.y + 1) * ATT_QTILE);
-  for (int t = blockIdx.y * ATT_QTILE + warp; t < q_end; t += ATT_WARPS) {
-    const T* qr = qkv + (row0 + t) * ld_qkv + colq;
-    for (int c = lane; c < ch; c += 32) Q[c] = Elem<T>::ld(qr + c) * scale;
+  for (int t0 = blockIdx.y * ATT_QTILE + warp * ATT_QB; t0 < q_end; t0 += ATT_WARPS * ATT_QB) {
+    const int nq = min(ATT_QB, q_end - t0);
+    for (int i = lane; i < ATT_QB * ch; i += 32) {
+      const int qi = i / ch, c = i - qi * ch;
+      Q[i] = qi < nq ? Elem<T>::ld(qkv + (row0 + t0 + qi) * ld_qkv + colq + c) * scale : 0.0f;
+    }
     __syncwarp();
-    float mx = -INFINITY;
+    float mx[ATT_QB];
+#pragma unroll
+    for (int qi = 0; qi < ATT_QB; ++qi) mx[qi] = -INFINITY;
     for (int s = lane; s < tokens; s += 32) {
-      const float* kr = Ks + s * kst;
-      float d = 0.0f;
-      for (int c = 0; c < ch; ++c) d = fmaf(Q[c], kr[c], d);
-      P[s] = d;
-      mx = fmaxf(mx, d);
+      const float4* kr = reinterpret_cast<const float4*>(Ks + s * kst);
+      float d[ATT_QB];
+#pragma unroll
+      for (int qi = 0; qi < ATT_QB; ++qi) d[qi] = 0.0f;
+      for (int c4 = 0; c4 < ch / 4; ++c4) {
+        const float4 kv = kr[c4];
+#pragma unroll
+        for (int qi = 0; qi < ATT_QB; ++qi) {
+          const float4 qv = reinterpret_cast<const float4*>(Q + qi * ch)[c4];
+          d[qi] = fmaf(qv.x, kv.x, fmaf(qv.y, kv.y, fmaf(qv.z, kv.z, fmaf(qv.w, kv.w, d[qi]))));
+        }
+      }
+      *reinterpret_cast<float4*>(P + s * ATT_QB) = make_float4(d[0], d[1], d[2], d[3]);
+#pragma unroll
+      for (int qi = 0; qi < ATT_QB; ++qi) mx[qi] = fmaxf(mx[qi], d[qi]);
+    }
+    float sum[ATT_QB];
+#pragma unroll
+    for (int qi = 0; qi < ATT_QB; ++qi) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx[qi] = fmaxf(mx[qi], __shfl_xor_sync(0xffffffffu, mx[qi], o));
+      sum[qi] = 0.0f;
+    }
+    for (int s = lane; s < tokens; s += 32) {
+      float4 pv = *reinterpret_cast<float4*>(P + s * ATT_QB);
+      pv.x = __expf(pv.x - mx[0]); pv.y = __expf(pv.y - mx[1]); pv.z = __expf(pv.z - mx[2]); pv.w = __expf(pv.w - mx[3]);
+      *reinterpret_cast<float4*>(P + s * ATT_QB) = pv;
+      sum[0] += pv.x; sum[1] += pv.y; sum[2] += pv.z; sum[3] += pv.w;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.0f;
-    for (int s = lane; s < tokens; s += 32) {
-      const float e = __expf(P[s] - mx);
-      P[s] = e;
-      sum += e;
-    }
+    for (int qi = 0; qi < ATT_QB; ++qi) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      for (int o = 16; o > 0; o >>= 1) sum[qi] += __shfl_xor_sync(0xffffffffu, sum[qi], o);
+    }
     __syncwarp();
-    const float inv = 1.0f / sum;
-    T* orow = out + (row0 + t) * ld_out + h * ch;
     for (int c = lane; c < ch; c += 32) {
-      float a = 0.0f;
-      for (int s = 0; s < tokens; ++s) a = fmaf(P[s], Vs[s * kst + c], a);
-      Elem<T>::st(orow + c, a * inv);
+      float a[ATT_QB];
+#pragma unroll
+      for (int qi = 0; qi < ATT_QB; ++qi) a[qi] = 0.0f;
+      for (int s = 0; s < tokens; ++s) {
+        const float v = Vs[s * kst + c];
+        const float4 pv = *reinterpret_cast<const float4*>(P + s * ATT_QB);
+        a[0] = fmaf(pv.x, v, a[0]); a[1] = fmaf(pv.y, v, a[1]); a[2] = fmaf(pv.z, v, a[2]); a[3] = fmaf(pv.w, v, a[3]);
+      }
+#pragma unroll
+      for (int qi = 0; qi < ATT_QB; ++qi)
+        if (qi < nq) Elem<T>::st(out + (row0 + t0 + qi) * ld_out + h * ch + c, a[qi] / sum[qi]);
     }
     __syncwarp();
   }
@@ -81,7 +111,8 @@ extern "C" int of_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t 
   using namespace of;
   OF_REQUIRE(qkv && out && batch > 0 && tokens > 0 && heads > 0 && ch > 0, "of_attention: bad arguments");
   OF_REQUIRE(dtype == OF_F32 || dtype == OF_BF16, "of_attention: bad dtype");
-  const size_t smem = ((size_t)2 * tokens * (ch + 1) + (size_t)ATT_WARPS * tokens + (size_t)ATT_WARPS * ch) * 4;
+  OF_REQUIRE(ch % 4 == 0, "of_attention: ch must be a multiple of 4");
+  const size_t smem = ((size_t)2 * tokens * (ch + 4) + (size_t)ATT_WARPS * tokens * ATT_QB + (size_t)ATT_WARPS * ATT_QB * ch) * 4;
   if (smem > 220 * 1024) {
     set_error("of_attention: T=%d ch=%d needs %zu B of shared memory (> 220 KB)", tokens, ch, smem);
     return OF_E_UNSUPPORTED;

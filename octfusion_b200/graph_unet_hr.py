@@ -10,7 +10,7 @@ import torch.nn as nn
 from . import ops
 from .ops import PreparedWeight
 from .modules import (GraphConv, GraphResBlockEmbed, GraphDownsample, GraphUpsample, graphnormalization,
-                      zero_module)
+                      zero_module, BatchedEmbedding)
 
 
 class _Linear(nn.Linear):
@@ -88,6 +88,13 @@ class UNet3DModel(nn.Module):
             'must specify label if and only if the model is class-conditional'
         bsz = doctree.batch_size
         emb = self.embed(timesteps, label)
+        if not hasattr(self, '_batched_emb'):
+            blocks = [m for m in self.input_blocks if isinstance(m, GraphResBlockEmbed)]
+            blocks += [self.middle_block1, self.middle_block2]
+            blocks += [m for m in self.output_blocks if isinstance(m, GraphResBlockEmbed)]
+            self._emb_blocks = blocks
+            self._batched_emb = BatchedEmbedding([m.emb_layers[1] for m in blocks])
+        es = {id(m): e for m, e in zip(self._emb_blocks, self._batched_emb(emb))}
         d = self.input_depth
         hs = []
         h = x.contiguous()
@@ -96,7 +103,7 @@ class UNet3DModel(nn.Module):
         hs.append(h)
         for module in self.input_blocks[1:]:
             if isinstance(module, GraphResBlockEmbed):
-                h = module.run(h, emb, doctree.plan[d], bsz)
+                h = module.run(h, emb, doctree.plan[d], bsz, e=es[id(module)])
             elif isinstance(module, GraphDownsample):
                 h = module(h, doctree, d)
                 d -= 1
@@ -104,12 +111,12 @@ class UNet3DModel(nn.Module):
                 h = module.run(h, doctree.plan[d])
             hs.append(h)
         if unet_lr is not None:
-            h = self.middle_block1.run(h, emb, doctree.plan[d], bsz)
+            h = self.middle_block1.run(h, emb, doctree.plan[d], bsz, e=es[id(self.middle_block1)])
             h_lr = unet_lr.forward_as_middle(h, doctree, timesteps, label, context)
-            h = self.middle_block2.run(h, emb, doctree.plan[d], bsz, x1=h_lr)
+            h = self.middle_block2.run(h, emb, doctree.plan[d], bsz, x1=h_lr, e=es[id(self.middle_block2)])
         for module in self.output_blocks:
             if isinstance(module, GraphResBlockEmbed):
-                h = module.run(h, emb, doctree.plan[d], bsz, x1=hs.pop())
+                h = module.run(h, emb, doctree.plan[d], bsz, x1=hs.pop(), e=es[id(module)])
             else:
                 h = module(h, doctree, d)
                 d += 1

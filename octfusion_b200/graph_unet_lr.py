@@ -15,7 +15,7 @@ import torch.nn as nn
 from . import ops
 from .modules import (ResnetBlock, ConvDownsample, ConvUpsample, NormActAttention, LearnedSinusoidalPosEmb,
                       convnormalization, activation_function, our_Identity, conv_nd, DenseTables,
-                      _to_morton, _from_morton)
+                      _to_morton, _from_morton, BatchedEmbedding)
 from .graph_unet_hr import _Linear
 
 
@@ -85,21 +85,26 @@ class UNet3DModel(nn.Module):
         t = self.tables(batch, x.device)
         r = res_log2
         emb = self.embed(timesteps, label)
+        if not hasattr(self, '_batched_emb'):
+            blocks = [m[0] for m in self.downs] + [self.mid_block1, self.mid_block2] + [m[0] for m in self.ups]
+            self._emb_blocks = blocks
+            self._batched_emb = BatchedEmbedding([m.time_mlp[1] for m in blocks])
+        es = {id(m): e for m, e in zip(self._emb_blocks, self._batched_emb(emb))}
         skips = []
         for resnet, attn, down in self.downs:
-            x = resnet.run(x, emb, t, r)
+            x = resnet.run(x, emb, t, r, e=es[id(resnet)])
             if isinstance(attn, NormActAttention):
                 x = attn.run(x, batch, 8 ** r)
             skips.append(x)
             if isinstance(down, ConvDownsample):
                 x = down.run(x, t, r)
                 r -= 1
-        x = self.mid_block1.run(x, emb, t, r)
+        x = self.mid_block1.run(x, emb, t, r, e=es[id(self.mid_block1)])
         if isinstance(self.mid_self_attn, NormActAttention):
             x = self.mid_self_attn.run(x, batch, 8 ** r)
-        x = self.mid_block2.run(x, emb, t, r)
+        x = self.mid_block2.run(x, emb, t, r, e=es[id(self.mid_block2)])
         for resnet, attn, up in self.ups:
-            x = resnet.run(x, emb, t, r, x1=skips.pop())
+            x = resnet.run(x, emb, t, r, x1=skips.pop(), e=es[id(resnet)])
             if isinstance(attn, NormActAttention):
                 x = attn.run(x, batch, 8 ** r)
             if isinstance(up, ConvUpsample):

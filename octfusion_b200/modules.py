@@ -230,6 +230,29 @@ class TimestepBlock(nn.Module):
     pass
 
 
+class BatchedEmbedding:
+    """All `Linear(SiLU(emb))` projections of a network (reference modules.py:709-715 emb_layers, :479-482
+    time_mlp) depend only on the timestep embedding, so they are evaluated by ONE launch over the row-wise
+    concatenation of their weights; each block then reads its column slice."""
+
+    def __init__(self, linears):
+        self.linears = list(linears)
+        self._key, self._w, self._b, self._off = None, None, None, None
+
+    def __call__(self, emb):
+        key = tuple((l.weight.data_ptr(), l.weight._version, l.bias._version) for l in self.linears)
+        if key != self._key:
+            self._w = torch.cat([l.weight.detach().float() for l in self.linears], 0).contiguous()
+            self._b = torch.cat([l.bias.detach().float() for l in self.linears], 0).contiguous()
+            off, self._off = 0, []
+            for l in self.linears:
+                self._off.append((off, off + l.weight.shape[0]))
+                off += l.weight.shape[0]
+            self._key = key
+        e = ops.linear_small(emb, self._w, self._b, a_silu=True)
+        return [e[:, a:b] for a, b in self._off]
+
+
 def _concat_rows(x0, x1):
     """materialise (x0 | x1) -- only needed where the concatenation itself is the residual."""
     n, c0, c1 = x0.shape[0], x0.shape[1], x1.shape[1]
@@ -266,11 +289,13 @@ class GraphResBlockEmbed(TimestepBlock):
             self.skip_connection = Conv1x1(self.channels, self.out_channels)
         self._pw_emb = PreparedWeight(1, emb_channels, 0, self.out_channels)
 
-    def run(self, x0, emb, plan, batch_size, x1=None):
-        """x = (x0 | x1) virtual concat; emb fp32 [B, emb_channels]."""
+    def run(self, x0, emb, plan, batch_size, x1=None, e=None):
+        """x = (x0 | x1) virtual concat; emb fp32 [B, emb_channels]; e = Linear(SiLU(emb)) when the caller has
+        already computed it for all blocks in one launch (BatchedEmbedding)."""
         h = self.block1_norm.run(x0, plan, batch_size, x1=x1, act=True)
         lin = self.emb_layers[1]
-        e = ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
+        if e is None:
+            e = ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
         h = self.conv1.run(h, plan, row_add=e, row_add_idx=plan.batch_id)
         h = self.block2_norm.run(h, plan, batch_size, act=True)
         if isinstance(self.skip_connection, Conv1x1):
@@ -458,12 +483,12 @@ class ResnetBlock(nn.Module):
         self.res_conv = conv_nd(world_dims, dim_in, dim_out, 1) if dim_in != dim_out else nn.Identity()
         self._pw_t = PreparedWeight(1, emb_dim, 0, dim_out)
 
-    def run(self, x0, emb, tables, res_log2, x1=None):
+    def run(self, x0, emb, tables, res_log2, x1=None, e=None):
         b, v = tables.batch, 8 ** res_log2
         tap = tables.conv(res_log2)
         h = self.block1[0].run(x0, b, v, x1=x1, act=True)
         lin = self.time_mlp[1]
-        t = ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
+        t = e if e is not None else ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
         h = self.block1[2].run(h, tap, row_add=t, row_add_idx=tables.sample_id(res_log2))
         h = self.block2[0].run(h, b, v, act=True)
         if isinstance(self.res_conv, nn.Identity):
