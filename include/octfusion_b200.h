@@ -89,6 +89,9 @@ typedef struct of_gemm_args {
    * by of_gather_mean_rows); multi_types[ord] = per-type neighbour counts, 8 bits per type.            */
   const void* a_multi; int64_t ld_multi;
   const uint64_t* multi_types;
+  /* row counts of a0 / a1 (tcgen05 path): > 0 enables the TMA gather4 half of the gather (rows beyond the
+   * count are the hardware's zero fill for empty slots); 0 = unknown -> cp.async only                       */
+  int32_t rows_a0, rows_a1;
 } of_gemm_args;
 
 /* CUDA-core FFMA path: any shape, fp32-exact accumulation order-insensitive to 1e-6. */

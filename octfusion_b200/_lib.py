@@ -36,6 +36,7 @@ class GemmArgs(C.Structure):
         ('dtype', _i32),
         ('a_multi', _vp), ('ld_multi', _i64),
         ('multi_types', _vp),
+        ('rows_a0', _i32), ('rows_a1', _i32),
     ]
 
 

@@ -25,6 +25,8 @@
 // type fractions; the weights are re-laid once by of_pack_weight_tc.
 #include "common.cuh"
 #include <stdlib.h>
+#include <string.h>
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace of {
 
@@ -82,6 +84,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// TMA gather4: four arbitrary rows x 64 columns (4 x 128 B) of a 2-D tensor -> 512 contiguous bytes of shared
+// memory, 128B-swizzled by the hardware; rows outside the tensor are zero-filled.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tmap, int col, int r0, int r1, int r2, int r3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t result_slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(result_slot), "r"(cols)
@@ -190,6 +204,8 @@ struct TcParams {
   int cblocks;       // (c0+c1)/64
   int npad;          // N rounded up to 16 (rows per K block in the packed weight image)
   int m_tiles, n_tiles;
+  int use_tma;       // 1: half of the row groups of every feature K block are fetched by TMA gather4
+  int rows0, rows1;  // row counts of a0 / a1 (TMA out-of-bounds row = zero fill for empty slots)
   int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA
 };
 
@@ -197,7 +213,9 @@ struct TcParams {
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcParams p,
+                                                                       const __grid_constant__ CUtensorMap tmap0,
+                                                                       const __grid_constant__ CUtensorMap tmap1) {
   using Cfg = TcCfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -433,18 +451,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 #pragma unroll
             for (int i = 0; i < TC_BM / 8; ++i) t[i] = 0;          // timing experiment: pure L1 hits
           }
-          // 16 asynchronous 16-byte global->shared copies back to back (no registers, no waiting):
-          // one neighbour -> its row; none -> zero fill; several -> the pre-averaged row of a_multi
           const __nv_bfloat16* msrc = reinterpret_cast<const __nv_bfloat16*>(g.a_multi) + ch + q * 8;
+          // Two independent data paths share the gather.  Rows 8i+0..3 (i = 0..15) of the tile: TMA gather4 --
+          // one instruction moves four source rows x 128 B and swizzles in hardware; the four row indices are
+          // held by lanes q, q+8, q+16, q+24 of the group's first warp.  Rows 8i+4..7: 16-byte cp.async
+          // (LDGSTS) through L1.  Either path alone saturates at ~16 KB/us per SM (request queues), together
+          // they overlap.
+          const bool tma_rows = p.use_tma && rbase < 4;           // this thread's rows belong to the TMA half
+          if (p.use_tma && gt < 32) {                             // first warp of the group: all 32 lanes converge
+            const CUtensorMap* tm = ch < g.c0 ? &tmap0 : &tmap1;
+            const int col = ch < g.c0 ? ch : ch - g.c0;
+            const int oob = ch < g.c0 ? p.rows0 : p.rows1;
 #pragma unroll
-          for (int i = 0; i < TC_BM / 8; ++i) {
-            const int rr = rbase + 8 * i;
-            const uint32_t dst = a_addr + rr * 128 + ((q ^ (rr & 7)) << 4);
-            const int32_t tv = t[i];
-            const void* sp = tv >= 0 ? (const void*)(src + (int64_t)tv * ld)
-                                     : (tv == -1 ? (const void*)src : (const void*)(msrc + (int64_t)(-(tv + 2)) * g.ld_multi));
-            if (p.debug & 128) cp_async_16_ca(dst, sp, tv == -1 ? 0u : 16u);
-            else cp_async_16(dst, sp, tv == -1 ? 0u : 16u);
+            for (int i = 0; i < TC_BM / 8; ++i) {
+              const int t1 = __shfl_sync(0xffffffffu, t[i], q + 8);
+              const int t2 = __shfl_sync(0xffffffffu, t[i], q + 16);
+              const int t3 = __shfl_sync(0xffffffffu, t[i], q + 24);
+              if (rbase == 0 && (i & 7) == q) {                   // lane q issues groups i = q and q + 8
+                const int t0 = t[i];
+                const uint32_t dst = a_addr + (8 * i) * 128;
+                if (t0 >= -1 && t1 >= -1 && t2 >= -1 && t3 >= -1) {
+                  mbar_expect_tx(bar_full + 8 * stage, 512u);
+                  tma_gather4(dst, tm, col, t0 < 0 ? oob : t0, t1 < 0 ? oob : t1, t2 < 0 ? oob : t2, t3 < 0 ? oob : t3,
+                              bar_full + 8 * stage);
+                } else {
+                  // a multi-neighbour slot in the group: its pre-averaged row lives in another tensor -> LDGSTS
+                  const int tt[4] = {t0, t1, t2, t3};
+                  const __nv_bfloat16* s0 = src - q * 8;
+                  const __nv_bfloat16* m0p = msrc - q * 8;
+#pragma unroll
+                  for (int r4 = 0; r4 < 4; ++r4) {
+                    const int rr = 8 * i + r4;
+                    const int tv = tt[r4];
+                    const __nv_bfloat16* base = tv >= 0 ? s0 + (int64_t)tv * ld
+                                                        : (tv == -1 ? s0 : m0p + (int64_t)(-(tv + 2)) * g.ld_multi);
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8)
+                      cp_async_16(a_addr + rr * 128 + ((c8 ^ (rr & 7)) << 4), base + c8 * 8, tv == -1 ? 0u : 16u);
+                  }
+                }
+              }
+            }
+          }
+          if (!tma_rows) {
+            // 16 asynchronous 16-byte global->shared copies back to back (no registers, no waiting):
+            // one neighbour -> its row; none -> zero fill; several -> the pre-averaged row of a_multi
+#pragma unroll
+            for (int i = 0; i < TC_BM / 8; ++i) {
+              const int rr = rbase + 8 * i;
+              const uint32_t dst = a_addr + rr * 128 + ((q ^ (rr & 7)) << 4);
+              const int32_t tv = t[i];
+              const void* sp = tv >= 0 ? (const void*)(src + (int64_t)tv * ld)
+                                       : (tv == -1 ? (const void*)src : (const void*)(msrc + (int64_t)(-(tv + 2)) * g.ld_multi));
+              if (p.debug & 128) cp_async_16_ca(dst, sp, tv == -1 ? 0u : 16u);
+              else cp_async_16(dst, sp, tv == -1 ? 0u : 16u);
+            }
           }
         } else {
           // node-type block: column tap*ntype + type holds (#neighbours of that type)/(#neighbours)
@@ -526,8 +587,39 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int taps, int
   }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, c] with row stride ld (elements); box = 64 columns x 1 row (the gather4 unit), 128B swizzle
+static bool make_row_tmap(CUtensorMap* m, const void* base, int64_t rows, int c, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || base == nullptr || rows <= 0) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)c, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN>
-static int launch_tc(const TcParams& p, cudaStream_t st) {
+static int launch_tc(const TcParams& p, const CUtensorMap& t0, const CUtensorMap& t1, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -540,8 +632,13 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
     configured = true;
   }
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  gather_gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  int grid = total < num_sms() ? total : num_sms();
+  {
+    static int lim = -1;                                   // OCTFUSION_TC_GRID: cap the CTA count (experiments)
+    if (lim < 0) { const char* e = getenv("OCTFUSION_TC_GRID"); lim = e ? atoi(e) : 0; }
+    if (lim > 0 && grid > lim) grid = lim;
+  }
+  gather_gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, t0, t1);
   OF_LAUNCH_CHECK("of_gather_gemm_tc");
   return OF_OK;
 }
@@ -603,11 +700,24 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
   p.npad = (a.N + 15) / 16 * 16;
   p.m_tiles = (a.M + TC_BM - 1) / TC_BM;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // TMA gather4 path: needs the row counts of the sources (out-of-bounds row = zero fill) and a tensor map each
+  alignas(64) CUtensorMap t0, t1;
+  memset(&t0, 0, sizeof(t0)); memset(&t1, 0, sizeof(t1));
+  p.use_tma = 0; p.rows0 = a.rows_a0; p.rows1 = a.rows_a1;
+  {
+    // Measured on B200 (profiles/tc_gather_experiments_r01.md): routing half of the rows through TMA gather4
+    // is ~1.6x SLOWER than 16-byte cp.async for this access pattern, so it is opt-in (OCTFUSION_TC_TMA=1).
+    static int want_tma = -1;
+    if (want_tma < 0) { const char* e = getenv("OCTFUSION_TC_TMA"); want_tma = e ? atoi(e) : 0; }
+    if (want_tma && a.rows_a0 > 0 && (a.c1 == 0 || a.rows_a1 > 0) && make_row_tmap(&t0, a.a0, a.rows_a0, a.c0, a.lda0) &&
+        (a.c1 == 0 || make_row_tmap(&t1, a.a1, a.rows_a1, a.c1, a.lda1)))
+      p.use_tma = 1;
+  }
   // widest tile that divides the padded N: fewer re-gathers of A per output column
-  if (p.npad % 256 == 0) { p.n_tiles = p.npad / 256; return launch_tc<256>(p, st); }
-  if (p.npad % 128 == 0) { p.n_tiles = p.npad / 128; return launch_tc<128>(p, st); }
-  if (p.npad % 64 == 0)  { p.n_tiles = p.npad / 64;  return launch_tc<64>(p, st); }
-  if (p.npad % 32 == 0)  { p.n_tiles = p.npad / 32;  return launch_tc<32>(p, st); }
+  if (p.npad % 256 == 0) { p.n_tiles = p.npad / 256; return launch_tc<256>(p, t0, t1, st); }
+  if (p.npad % 128 == 0) { p.n_tiles = p.npad / 128; return launch_tc<128>(p, t0, t1, st); }
+  if (p.npad % 64 == 0)  { p.n_tiles = p.npad / 64;  return launch_tc<64>(p, t0, t1, st); }
+  if (p.npad % 32 == 0)  { p.n_tiles = p.npad / 32;  return launch_tc<32>(p, t0, t1, st); }
   p.n_tiles = p.npad / 16;
-  return launch_tc<16>(p, st);
+  return launch_tc<16>(p, t0, t1, st);
 }

@@ -160,6 +160,7 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g.a0, g.lda0, g.c0 = a0.data_ptr(), a0.stride(0), c0
     g.a1, g.lda1, g.c1 = (a1.data_ptr(), a1.stride(0), c1) if a1 is not None else (None, 0, 0)
     g.a_multi, g.ld_multi, g.multi_types = None, 0, None
+    g.rows_a0, g.rows_a1 = a0.shape[0], (a1.shape[0] if a1 is not None else 0)
     if tap is not None and use_tc:
         g.tap_tab = tap.tab_ord.data_ptr()
         if tap.n_multi > 0:
