@@ -75,6 +75,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// one lane of a fully converged warp (elect.sync): the uniform-datapath instructions (UTCHMMA, UTCBAR, UBLKCP)
+// are then issued from converged code instead of the ELECT/BRA.U.ANY retry loops the compiler emits for a
+// divergent `if (lane == 0)` region
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -176,6 +184,9 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint3
 __device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -191,7 +202,7 @@ struct TcCfg {
   static constexpr int A_BYTES = TC_BM * 128;                       // 16 KB
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN >= 256 ? 4 : BN >= 128 ? 5 : 6;
+  static constexpr int STAGES = BN >= 256 ? 4 : BN >= 128 ? 6 : 8;
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   static constexpr int TAP_BYTES = 0;                               // (tap table is read through L1)
   static constexpr int AUX_BYTES = 256;                             // mbarriers + tmem slot
@@ -327,7 +338,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     }
   } else if (warp == TC_EPI_WARPS) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // the whole warp walks the pipeline (all lanes wait on the barriers); one elected lane issues
+    {
       constexpr uint32_t idesc = make_idesc(BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -342,21 +354,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           tc_fence_after();
           const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            if (p.debug & 8) break;
-            umma_bf16(d_tmem, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              if (p.debug & 8) break;
+              umma_bf16(d_tmem, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_empty + 8 * stage);            // frees the smem stage when these MMAs retire
+            if (kb == p.num_kb - 1) umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
           }
-          umma_commit(bar_empty + 8 * stage);            // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * as);                 // accumulator complete -> epilogue
       }
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // =========================== weight loader ===========================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint8_t* wp = reinterpret_cast<const uint8_t*>(g.w);
@@ -365,11 +380,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t b_addr = stage_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
-          if (p.debug & 2) { mbar_arrive(bar_full + 8 * stage); }
-          else {
-            mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::B_BYTES);
-            bulk_g2s(b_addr, wp + ((int64_t)kb * p.npad + n0) * 128, Cfg::B_BYTES, bar_full + 8 * stage);
+          if (elect_one()) {
+            if (p.debug & 2) { mbar_arrive(bar_full + 8 * stage); }
+            else {
+              mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::B_BYTES);
+              bulk_g2s(b_addr, wp + ((int64_t)kb * p.npad + n0) * 128, Cfg::B_BYTES, bar_full + 8 * stage);
+            }
           }
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -543,8 +561,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         }
         // CUTLASS sm100 cp.async+UMMA protocol: one arrive that fires when this thread's cp.asyncs have
         // landed (self-incrementing, not counted) + one ordinary release-arrive (counted)
-        cp_async_mbar_arrive(bar_full + 8 * stage);
-        mbar_arrive(bar_full + 8 * stage);
+        // one counted arrival per thread: for gathered blocks it fires when this thread's cp.asyncs have landed
+        // (cp.async.mbarrier.arrive.noinc); for the node-type block (generic stores + proxy fence) a plain arrive
+        if (kb < p.cblocks * taps && !(p.debug & 1)) cp_async_mbar_arrive_noinc(bar_full + 8 * stage);
+        else mbar_arrive(bar_full + 8 * stage);
       }
     }
   }
