@@ -191,6 +191,9 @@ def workload_config(args, nodes):
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
+    # exactly ONE line may reach stdout (the JSON): NCCL / torch banners are sent to stderr for the whole run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -207,7 +210,7 @@ def run_ours(args):
     cfg = config_for(args)
     act = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
     net = randomise_(graph_unet_union.UNet3DModel('hr', **cfg), 0).to(dev).eval()
-    l4, l5 = synth_splits(args.batch, seed=rank)      # seed 0 = the octrees SURVEY.md section 8 sized
+    l4, l5 = synth_splits(args.batch, seed=0)         # same 32 shapes on every rank: identical per-GPU work (weak scaling)
     doc = DualOctree(octree_from_splits(l4, l5, args.batch, device=dev))
     nodes = {d: doc.plan[d].rows for d in range(4, 7)}
     n6, cc = doc.total_num, args.code_channels
@@ -313,8 +316,17 @@ def run_ours(args):
         tot_by = sum(a['bytes'] for a in agg.values())
         if tot_ms > 0:
             ach = tot_fl / (tot_ms * 1e-3) / 1e12
+            traffic = None
+            try:        # DRAM bytes of the same launches from the committed ncu capture (profiles/tc_traffic_r01.json)
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'tc_traffic_r01.json')))
+                traffic = tj['dram_bytes_per_step'] / tj['launches_per_step']
+            except Exception:  # noqa: BLE001
+                pass
+            nl = sum(a['launches'] for a in agg.values()) / reps
             roofline = {'kernel': 'gather_gemm_tc_kernel (all launches of one step)', 'bound': 'tensor',
-                        'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
+                        'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic,
+                        'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read+write, mean over the step)',
+                        'launches_per_step': nl, 'algorithmic_bytes_per_launch': tot_by / reps / max(nl, 1),
                         'peak_source': peak_src, 'ms_per_step_in_kernel': tot_ms / reps,
                         'algorithmic_gflop_per_step': tot_fl / reps / 1e9, 'algorithmic_gb_per_step': tot_by / reps / 1e9}
             per_layer = []
@@ -343,7 +355,7 @@ def run_ours(args):
             'roofline': roofline, 'cpu_baseline': cpu, 'gathered_latent_rows': [int(t.shape[0]) for t in gathered]}
     if per_layer:
         line['roofline_per_layer'] = per_layer[:12]
-    print(json.dumps(line))
+    os.write(real_stdout, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
