@@ -244,11 +244,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   const of_gemm_args& g = p.g;
   const int taps = g.taps;
   const int total_tiles = p.m_tiles * p.n_tiles;
-  // each CTA owns a CONTIGUOUS range of tiles (neighbouring rows: shared gather rows stay hot in L2, and the rows of
-  // consecutive tiles belong to the same sample, which lets the epilogue keep norm statistics in registers)
-  const int tq = total_tiles / (int)gridDim.x, tr = total_tiles % (int)gridDim.x;
-  const int my_tiles = tq + ((int)blockIdx.x < tr ? 1 : 0);
-  const int first_tile = (int)blockIdx.x * tq + min((int)blockIdx.x, tr);
 
   if (warp == TC_EPI_WARPS && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -270,31 +265,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   if (warp < TC_EPI_WARPS) {
     // =========================== epilogue ===========================
     const int r = warp * 32 + lane;
-    // norm statistics of the output: lane j owns columns n0 + 32*chunk + j; sums stay in registers while the
-    // warp's rows stay inside one sample (and one column tile) and are flushed with fp64 atomics on a change
-    constexpr int NCH = BN >= 32 ? BN / 32 : 1;
-    float st_s[NCH], st_q[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) { st_s[c] = 0.0f; st_q[c] = 0.0f; }
-    int st_b = -1, st_n0 = 0;
-    auto flush_stats = [&]() {
-      if (st_b >= 0) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col = st_n0 + c * 32 + lane;
-          if (col < g.N) {
-            double* st = g.stats + ((int64_t)st_b * g.N + col) * 2;
-            atomicAdd(st, (double)st_s[c]);
-            atomicAdd(st + 1, (double)st_q[c]);
-          }
-          st_s[c] = 0.0f; st_q[c] = 0.0f;
-        }
-      }
-      st_b = -1;
-    };
     int it = 0;
-    for (; it < my_tiles; ++it) {
-      const int tile = first_tile + it;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * BN;
       const int as = it & 1;
       mbar_wait(bar_tfull + 8 * as, (it >> 1) & 1);
@@ -306,7 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       const __nv_bfloat16* res =
           (row_ok && g.resid) ? reinterpret_cast<const __nv_bfloat16*>(g.resid) + (int64_t)m * g.ld_resid : nullptr;
       constexpr int CH = BN >= 32 ? 32 : 16;
-#pragma unroll
+#pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         uint32_t acc[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c0);
@@ -368,14 +340,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
                 sq[k] = keep_q + __shfl_xor_sync(0xffffffffu, give_q, sft);
               }
             }
-            if (b0 >= 0) {
-              if (b0 != st_b || n0 != st_n0) { flush_stats(); st_b = b0; st_n0 = n0; }
-              st_s[c0 / 32] += sa[0];
-              st_q[c0 / 32] += sq[0];
+            if (b0 >= 0 && nb + lane < g.N) {
+              double* st = g.stats + ((int64_t)b0 * g.N + nb + lane) * 2;
+              atomicAdd(st, (double)sa[0]);
+              atomicAdd(st + 1, (double)sq[0]);
             }
-          } else {                                     // the warp's rows straddle a sample boundary (rare)
-            flush_stats();
-            for (int j = 0; j < 32 && row_ok; ++j) {
+          } else if (row_ok) {                         // the warp's rows straddle a sample boundary (rare)
+            for (int j = 0; j < 32; ++j) {
               if (nb + j < g.N) {
                 double* st = g.stats + ((int64_t)bsm * g.N + nb + j) * 2;
                 atomicAdd(st, (double)v[j]);
@@ -409,7 +380,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * as);
     }
-    if (g.stats != nullptr) flush_stats();
   } else if (warp == TC_EPI_WARPS) {
     // =========================== MMA issuer ===========================
     // the whole warp walks the pipeline (all lanes wait on the barriers); one elected lane issues
@@ -418,7 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (; it < my_tiles; ++it) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         mbar_wait(bar_tempty + 8 * as, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -449,8 +419,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       int stage = 0;
       uint32_t phase = 0;
       const uint8_t* wp = reinterpret_cast<const uint8_t*>(g.w);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int tile = first_tile + it;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -483,12 +452,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     // K blocks of this CTA in consumption order: kbg = tile_iter * num_kb + kb; this group owns kbg = grp (mod 4).
     // The 16 table entries of the NEXT owned block are fetched before waiting for the current stage to be
     // released, which takes the table latency off the stage turnaround.
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t kb_total = (uint32_t)my_tiles * (uint32_t)p.num_kb;
     const int feat_kb = p.cblocks * taps;
     auto fetch_taps = [&](uint32_t kk, int32_t* t) {
       const int tile_iter = (int)(kk / (uint32_t)p.num_kb);
       const int kb = (int)(kk - (uint32_t)tile_iter * (uint32_t)p.num_kb);
-      const int tile = first_tile + tile_iter;
+      const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
       const int m0 = (tile / p.n_tiles) * TC_BM;
       if (kb >= feat_kb) return;
       const int tap = kb % taps;
@@ -521,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       {
         const int tile_iter = (int)(kbg / (uint32_t)p.num_kb);
         const int kb = (int)(kbg - (uint32_t)tile_iter * (uint32_t)p.num_kb);
-        const int tile = first_tile + tile_iter;
+        const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
         const int m0 = (tile / p.n_tiles) * TC_BM;
         int32_t t[TC_BM / 8];
 #pragma unroll
