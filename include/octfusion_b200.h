@@ -92,9 +92,6 @@ typedef struct of_gemm_args {
   /* row counts of a0 / a1 (tcgen05 path): > 0 enables the TMA gather4 half of the gather (rows beyond the
    * count are the hardware's zero fill for empty slots); 0 = unknown -> cp.async only                       */
   int32_t rows_a0, rows_a1;
-  /* tcgen05 path, optional: stats [B, N, 2] fp64 += per-(sample, channel) (sum, sum of squares) of the OUTPUT rows,
-   * sample = stats_idx[m] -- the statistics of the following group norm come out of the GEMM epilogue */
-  double* stats; const int32_t* stats_idx;
 } of_gemm_args;
 
 /* CUDA-core FFMA path: any shape, fp32-exact accumulation order-insensitive to 1e-6. */
@@ -132,11 +129,6 @@ int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t
 int of_gn_finalize(const double* sums, const int32_t* rows_of_sample, int32_t rows_per_sample,
                    const float* gamma, const float* beta, int32_t batch, int32_t channels,
                    int32_t groups, float eps, float count_eps, float* scale, float* shift, void* stream);
-/* scale / shift from PER-CHANNEL statistics [B, c, 2] fp64 of up to two concatenated sources (produced by the
- * of_gather_gemm_tc epilogue); same arithmetic as of_gn_finalize after summing the channels of each group */
-int of_gn_finalize_ch(const double* st0, int32_t c0, const double* st1, int32_t c1, const int32_t* rows_of_sample,
-                      int32_t rows_per_sample, const float* gamma, const float* beta, int32_t batch, int32_t groups,
-                      float eps, float count_eps, float* scale, float* shift, void* stream);
 int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                 const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
                 const float* scale, const float* shift, int32_t act, int32_t dtype,

@@ -37,7 +37,6 @@ class GemmArgs(C.Structure):
         ('a_multi', _vp), ('ld_multi', _i64),
         ('multi_types', _vp),
         ('rows_a0', _i32), ('rows_a1', _i32),
-        ('stats', _vp), ('stats_idx', _vp),
     ]
 
 
@@ -62,7 +61,6 @@ _PROTOS = {
     'of_repack_weight': (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
     'of_gn_stats': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp]),
     'of_gn_finalize': (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp]),
-    'of_gn_finalize_ch': (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _f32, _f32, _vp, _vp, _vp]),
     'of_gn_apply': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     'of_attention': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     'of_linear_small': (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),

@@ -284,8 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c0);
         if (CH == 32) { OF_TMEM_LD32(taddr, acc); } else { OF_TMEM_LD16(taddr, acc); }
         tmem_ld_wait();
-        const bool want_stats = (g.stats != nullptr) && CH == 32;
-        if ((!row_ok && !want_stats) || (p.debug & 4)) continue;
+        if (!row_ok || (p.debug & 4)) continue;
         const int nb = n0 + c0;
         float v[32];
 #pragma unroll
@@ -312,49 +311,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 #pragma unroll
             for (int j = 0; j < CH; ++j) if (nb + j < g.N) v[j] += __bfloat162float(res[nb + j]);
           }
-        }
-        if (want_stats) {
-          // per-(sample, channel) sum and sum of squares of the OUTPUT, for the group norm that follows
-          // (reference modules.py:291-326 re-reads the tensor three times for this).  Column sums over the 32 rows
-          // of the warp by a transpose-reduce: 31 shuffles per statistic, lane j ends up owning column nb + j.
-          const int bsm = row_ok ? g.stats_idx[m] : -1;
-          const int b0 = __shfl_sync(0xffffffffu, bsm, 0);
-          const bool uniform = __all_sync(0xffffffffu, bsm == b0 || bsm < 0);
-          if (uniform) {
-            float sa[32], sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = (row_ok && (full || nb + j < g.N)) ? v[j] : 0.0f;
-              sa[j] = x; sq[j] = x * x;
-            }
-#pragma unroll
-            for (int sft = 16; sft >= 1; sft >>= 1) {
-              const bool up = (lane & sft) != 0;
-#pragma unroll
-              for (int k = 0; k < sft; ++k) {
-                const float give_a = up ? sa[k] : sa[k + sft];
-                const float keep_a = up ? sa[k + sft] : sa[k];
-                const float give_q = up ? sq[k] : sq[k + sft];
-                const float keep_q = up ? sq[k + sft] : sq[k];
-                sa[k] = keep_a + __shfl_xor_sync(0xffffffffu, give_a, sft);
-                sq[k] = keep_q + __shfl_xor_sync(0xffffffffu, give_q, sft);
-              }
-            }
-            if (b0 >= 0 && nb + lane < g.N) {
-              double* st = g.stats + ((int64_t)b0 * g.N + nb + lane) * 2;
-              atomicAdd(st, (double)sa[0]);
-              atomicAdd(st + 1, (double)sq[0]);
-            }
-          } else if (row_ok) {                         // the warp's rows straddle a sample boundary (rare)
-            for (int j = 0; j < 32; ++j) {
-              if (nb + j < g.N) {
-                double* st = g.stats + ((int64_t)bsm * g.N + nb + j) * 2;
-                atomicAdd(st, (double)v[j]);
-                atomicAdd(st + 1, (double)v[j] * (double)v[j]);
-              }
-            }
-          }
-          if (!row_ok) continue;
         }
         if (g.out_f32) {
           float* o = reinterpret_cast<float*>(g.out) + orow * g.ldo + nb;

@@ -153,32 +153,6 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, const int32_
   shift[i] = (float)((double)beta[c] - m * rstd * ga);
 }
 
-__global__ void gn_finalize_ch_kernel(const double* __restrict__ st0, int c0, const double* __restrict__ st1, int c1,
-                                      const int32_t* __restrict__ rows_of_sample, int rows_per_sample,
-                                      const float* __restrict__ gamma, const float* __restrict__ beta, int batch,
-                                      int groups, float eps, float count_eps, float* __restrict__ scale,
-                                      float* __restrict__ shift) {
-  const int C = c0 + c1;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= batch * C) return;
-  const int b = i / C, c = i - b * C;
-  const int cpg = C / groups, g = c / cpg;
-  double S = 0.0, Q = 0.0;
-  for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
-    const double* p = k < c0 ? st0 + ((int64_t)b * c0 + k) * 2 : st1 + ((int64_t)b * c1 + (k - c0)) * 2;
-    S += p[0]; Q += p[1];
-  }
-  const double n = (double)(rows_of_sample ? rows_of_sample[b] : rows_per_sample) * (double)cpg;
-  const double inv = 1.0 / (n + (double)count_eps);
-  const double m = S * inv;
-  double var = (Q - 2.0 * m * S + n * m * m) * inv;
-  if (var < 0.0) var = 0.0;
-  const double rstd = 1.0 / sqrt(var + (double)eps);
-  const double ga = gamma[c];
-  scale[i] = (float)(rstd * ga);
-  shift[i] = (float)((double)beta[c] - m * rstd * ga);
-}
-
 template <typename T> struct FastAct;
 template <> struct FastAct<float> { static __device__ __forceinline__ float silu(float v) { return silu_f(v); } };
 template <> struct FastAct<__nv_bfloat16> { static __device__ __forceinline__ float silu(float v) { return silu_fast(v); } };
@@ -283,21 +257,6 @@ extern "C" int of_gn_finalize(const double* sums, const int32_t* rows_of_sample,
   gn_finalize_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       sums, rows_of_sample, rows_per_sample, gamma, beta, batch, channels, groups, eps, count_eps, scale, shift);
   OF_LAUNCH_CHECK("of_gn_finalize");
-  return OF_OK;
-}
-
-extern "C" int of_gn_finalize_ch(const double* st0, int32_t c0, const double* st1, int32_t c1,
-                                 const int32_t* rows_of_sample, int32_t rows_per_sample, const float* gamma,
-                                 const float* beta, int32_t batch, int32_t groups, float eps, float count_eps,
-                                 float* scale, float* shift, void* stream) {
-  using namespace of;
-  OF_REQUIRE(st0 && c0 > 0 && ((st1 == nullptr) == (c1 == 0)) && gamma && beta && scale && shift, "of_gn_finalize_ch: bad arguments");
-  OF_REQUIRE(groups > 0 && (c0 + c1) % groups == 0, "of_gn_finalize_ch: bad groups");
-  OF_REQUIRE(rows_of_sample != nullptr || rows_per_sample > 0, "of_gn_finalize_ch: need a row count");
-  const int n = batch * (c0 + c1);
-  gn_finalize_ch_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      st0, c0, st1, c1, rows_of_sample, rows_per_sample, gamma, beta, batch, groups, eps, count_eps, scale, shift);
-  OF_LAUNCH_CHECK("of_gn_finalize_ch");
   return OF_OK;
 }
 

@@ -99,7 +99,7 @@ class UNet3DModel(nn.Module):
         hs = []
         h = x.contiguous()
         if not as_middle:
-            h = self.input_blocks[0].run(h, doctree.plan[d], stats_idx=doctree.plan[d].batch_id, stats_batch=bsz)
+            h = self.input_blocks[0].run(h, doctree.plan[d])
         hs.append(h)
         for module in self.input_blocks[1:]:
             if isinstance(module, GraphResBlockEmbed):

@@ -94,19 +94,19 @@ class UNet3DModel(nn.Module):
         for resnet, attn, down in self.downs:
             x = resnet.run(x, emb, t, r, e=es[id(resnet)])
             if isinstance(attn, NormActAttention):
-                x = attn.run(x, batch, 8 ** r, t.sample_id(r))
+                x = attn.run(x, batch, 8 ** r)
             skips.append(x)
             if isinstance(down, ConvDownsample):
                 x = down.run(x, t, r)
                 r -= 1
         x = self.mid_block1.run(x, emb, t, r, e=es[id(self.mid_block1)])
         if isinstance(self.mid_self_attn, NormActAttention):
-            x = self.mid_self_attn.run(x, batch, 8 ** r, t.sample_id(r))
+            x = self.mid_self_attn.run(x, batch, 8 ** r)
         x = self.mid_block2.run(x, emb, t, r, e=es[id(self.mid_block2)])
         for resnet, attn, up in self.ups:
             x = resnet.run(x, emb, t, r, x1=skips.pop(), e=es[id(resnet)])
             if isinstance(attn, NormActAttention):
-                x = attn.run(x, batch, 8 ** r, t.sample_id(r))
+                x = attn.run(x, batch, 8 ** r)
             if isinstance(up, ConvUpsample):
                 x = up.run(x, t, r)
                 r += 1

@@ -200,7 +200,7 @@ class GraphDownsample(nn.Module):
         # epilogue scatters the result to the parent's row
         xd = x[pd.leaf_base:].view(-1, 8 * c)
         ops.gather_gemm(xd, self.downsample.prepared(), out=mid, out_rows=pd.down_out_rows)
-        return self.conv.run(mid, pc, stats_idx=pc.batch_id, stats_batch=doctree.batch_size)
+        return self.conv.run(mid, pc)
 
 
 class GraphUpsample(nn.Module):
@@ -223,7 +223,7 @@ class GraphUpsample(nn.Module):
         # result *is* the [8M, C] block of children rows, written in place
         tail = mid[pc.up_copy_rows:]
         ops.gather_gemm(x, self.upsample.prepared(), in_rows=pc.up_in_rows, out=tail, ldo=8 * c)
-        return self.conv.run(mid, pf, stats_idx=pf.batch_id, stats_batch=doctree.batch_size)
+        return self.conv.run(mid, pf)
 
 
 class TimestepBlock(nn.Module):
@@ -296,7 +296,7 @@ class GraphResBlockEmbed(TimestepBlock):
         lin = self.emb_layers[1]
         if e is None:
             e = ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
-        h = self.conv1.run(h, plan, row_add=e, row_add_idx=plan.batch_id, stats_idx=plan.batch_id, stats_batch=batch_size)
+        h = self.conv1.run(h, plan, row_add=e, row_add_idx=plan.batch_id)
         h = self.block2_norm.run(h, plan, batch_size, act=True)
         if isinstance(self.skip_connection, Conv1x1):
             skip = self.skip_connection.run(x0, x1)
@@ -304,7 +304,7 @@ class GraphResBlockEmbed(TimestepBlock):
             skip = x0
         else:
             skip = _concat_rows(x0, x1)          # identity skip of a concatenated input (e.g. 256+256 -> 512)
-        return self.conv2.run(h, plan, resid=skip, stats_idx=plan.batch_id, stats_batch=batch_size)
+        return self.conv2.run(h, plan, resid=skip)
 
     @torch.no_grad()
     def forward(self, x, emb, doctree, depth):
@@ -437,7 +437,7 @@ class ConvDownsample(nn.Module):
         self.op = conv_nd(dims, channels, channels, 3, stride=2, padding=1)
 
     def run(self, x, tables, res_log2):
-        return self.op.run(x, tables.down(res_log2 - 1), stats_idx=tables.sample_id(res_log2 - 1), stats_batch=tables.batch)
+        return self.op.run(x, tables.down(res_log2 - 1))
 
     @torch.no_grad()
     def forward(self, x):
@@ -456,7 +456,7 @@ class ConvUpsample(nn.Module):
         self.conv = conv_nd(dims, channels, channels, 3, padding=1)
 
     def run(self, x, tables, res_log2):
-        return self.conv.run(x, tables.up(res_log2 + 1), stats_idx=tables.sample_id(res_log2 + 1), stats_batch=tables.batch)
+        return self.conv.run(x, tables.up(res_log2 + 1))
 
     @torch.no_grad()
     def forward(self, x):
@@ -489,14 +489,13 @@ class ResnetBlock(nn.Module):
         h = self.block1[0].run(x0, b, v, x1=x1, act=True)
         lin = self.time_mlp[1]
         t = e if e is not None else ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
-        sid = tables.sample_id(res_log2)
-        h = self.block1[2].run(h, tap, row_add=t, row_add_idx=sid, stats_idx=sid, stats_batch=b)
+        h = self.block1[2].run(h, tap, row_add=t, row_add_idx=tables.sample_id(res_log2))
         h = self.block2[0].run(h, b, v, act=True)
         if isinstance(self.res_conv, nn.Identity):
             skip = x0 if x1 is None else _concat_rows(x0, x1)
         else:
             skip = ops.gather_gemm(x0, self.res_conv.prepared(), a1=x1, bias=self.res_conv.bias)
-        return self.block2[3].run(h, tap, resid=skip, stats_idx=sid, stats_batch=b)
+        return self.block2[3].run(h, tap, resid=skip)
 
     @torch.no_grad()
     def forward(self, x, time_emb, text_condition=None):
@@ -527,13 +526,11 @@ class AttentionBlock(nn.Module):
         self.attention = QKVAttention()
         self.proj_out = zero_module(conv_nd(1, channels, channels, 1))
 
-    def run(self, x, batch, tokens, sample_id=None):
+    def run(self, x, batch, tokens):
         """x [B*T, C] channels-last."""
         h = self.norm.run(x, batch, tokens)
         qkv = self.qkv.run(h)
         a = ops.attention(qkv, batch, tokens, self.num_heads)
-        if sample_id is not None:
-            return self.proj_out.run(a, resid=x, stats_idx=sample_id, stats_batch=batch)
         return self.proj_out.run(a, resid=x)
 
     @torch.no_grad()
@@ -552,8 +549,8 @@ class NormActAttention(nn.Sequential):
     def __init__(self, channels, num_heads):
         super().__init__(convnormalization(channels), activation_function(), AttentionBlock(channels, num_heads))
 
-    def run(self, x, batch, tokens, sample_id=None):
-        return self[2].run(self[0].run(x, batch, tokens, act=True), batch, tokens, sample_id)
+    def run(self, x, batch, tokens):
+        return self[2].run(self[0].run(x, batch, tokens, act=True), batch, tokens)
 
 
 class LearnedSinusoidalPosEmb(nn.Module):

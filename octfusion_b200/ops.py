@@ -12,7 +12,6 @@ from . import _lib
 from ._lib import lib, ptr, stream, check, dt, GemmArgs
 
 _FORCE_SIMT = os.environ.get('OCTFUSION_B200_FORCE_SIMT', '0') == '1'
-_NO_FUSED_STATS = os.environ.get('OCTFUSION_B200_NO_FUSED_STATS', '0') == '1'
 _PROFILE = None        # when a list: (kind, meta, start_event, end_event) per GEMM launch (bench.py roofline leg)
 
 
@@ -132,7 +131,7 @@ class PreparedWeight:
 
 def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows=None, node_type=None,
                 a_silu=False, bias=None, row_add=None, row_add_idx=None, resid=None, out_rows=None,
-                out=None, ldo=None, out_f32=False, m=None, force_simt=False, stats_idx=None, stats_batch=0):
+                out=None, ldo=None, out_f32=False, m=None, force_simt=False):
     """out[m,:] = sum_tap mean_nbr [a0|a1|onehot] . W[tap] + bias + row_add[row_add_idx[m]] + resid[m]."""
     _lib.require_cuda(a0, a1, bias, row_add, resid, out)
     assert a0.dim() == 2 and a0.stride(1) == 1
@@ -162,13 +161,6 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g.a1, g.lda1, g.c1 = (a1.data_ptr(), a1.stride(0), c1) if a1 is not None else (None, 0, 0)
     g.a_multi, g.ld_multi, g.multi_types = None, 0, None
     g.rows_a0, g.rows_a1 = a0.shape[0], (a1.shape[0] if a1 is not None else 0)
-    # per-(sample, channel) statistics of the output from the GEMM epilogue (feeds the next group norm)
-    stats = None
-    if use_tc and stats_idx is not None and stats_batch > 0 and n >= 32 and out_rows is None and not _NO_FUSED_STATS:
-        stats = torch.zeros((stats_batch, n, 2), dtype=torch.float64, device=a0.device)
-        g.stats, g.stats_idx = stats.data_ptr(), stats_idx.data_ptr()
-    else:
-        g.stats, g.stats_idx = None, None
     if tap is not None and use_tc:
         g.tap_tab = tap.tab_ord.data_ptr()
         if tap.n_multi > 0:
@@ -217,8 +209,6 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
                          bytes=float(m * (c0 + c1) * es + m * n * (4 if g.out_f32 else es) + nnz * 4 + k * n * es
                                      + (m * n * es if resid is not None else 0)),
                          start=e0, end=e1))
-    if stats is not None:
-        out._of_stats = stats
     _trace('gemm_tc' if use_tc else 'gemm_simt', out)
     return out
 
@@ -245,26 +235,16 @@ def group_norm(x0, gamma, beta, groups: int, batch: int, *, x1=None, sample_id=N
     c1 = 0 if x1 is None else x1.shape[1]
     c = c0 + c1
     dev = x0.device
-    scale = torch.empty((batch, c), dtype=torch.float32, device=dev)
-    shift = torch.empty((batch, c), dtype=torch.float32, device=dev)
+    sums = torch.zeros((batch, groups, 2), dtype=torch.float64, device=dev)
     a1 = (ptr(x1), x1.stride(0), c1) if x1 is not None else (None, 0, 0)
     sid = ptr(sample_id) if sample_id is not None else None
-    st0 = getattr(x0, '_of_stats', None)
-    st1 = getattr(x1, '_of_stats', None) if x1 is not None else None
-    if (st0 is not None and tuple(st0.shape) == (batch, c0, 2) and
-            (x1 is None or (st1 is not None and tuple(st1.shape) == (batch, c1, 2)))):
-        # statistics already accumulated by the epilogue of the GEMM(s) that produced the input(s)
-        check(lib.of_gn_finalize_ch(ptr(st0), c0, ptr(st1) if x1 is not None else None, c1,
-                                    ptr(rows_of_sample) if rows_of_sample is not None else None, rows_per_sample,
-                                    ptr(gamma), ptr(beta), batch, groups, float(eps), float(count_eps), ptr(scale),
-                                    ptr(shift), stream()), 'of_gn_finalize_ch')
-    else:
-        sums = torch.zeros((batch, groups, 2), dtype=torch.float64, device=dev)
-        check(lib.of_gn_stats(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, batch, groups,
-                              dt(x0), ptr(sums), stream()), 'of_gn_stats')
-        check(lib.of_gn_finalize(ptr(sums), ptr(rows_of_sample) if rows_of_sample is not None else None, rows_per_sample,
-                                 ptr(gamma), ptr(beta), batch, c, groups, float(eps), float(count_eps), ptr(scale),
-                                 ptr(shift), stream()), 'of_gn_finalize')
+    check(lib.of_gn_stats(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, batch, groups,
+                          dt(x0), ptr(sums), stream()), 'of_gn_stats')
+    scale = torch.empty((batch, c), dtype=torch.float32, device=dev)
+    shift = torch.empty((batch, c), dtype=torch.float32, device=dev)
+    check(lib.of_gn_finalize(ptr(sums), ptr(rows_of_sample) if rows_of_sample is not None else None, rows_per_sample,
+                             ptr(gamma), ptr(beta), batch, c, groups, float(eps), float(count_eps), ptr(scale),
+                             ptr(shift), stream()), 'of_gn_finalize')
     if out is None:
         out = torch.empty((rows, c), dtype=x0.dtype, device=dev)
     check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, ptr(scale),

@@ -258,28 +258,3 @@ def test_graphconv_small_channel_input_padded_to_tc():
     for cin in (3, 8):
         y, ref32, refbf = _graphconv_case(2, 6, cin, 128, 5, torch.bfloat16)
         assert relerr(y, refbf) < 8e-3 and relerr(y, ref32) < 2e-2
-
-
-def test_fused_norm_statistics_from_gemm_epilogue():
-    """the tcgen05 epilogue accumulates per-(sample, channel) sum / sum of squares of its output; the group norm
-    that follows must give the same result as the stand-alone statistics kernel."""
-    from octfusion_b200.modules import GraphConv, DualOctreeGroupNorm
-    from octfusion_b200 import ops
-    dg, _ = oracle_doctree(3, 5)
-    doc = product_doctree(3, 5)
-    d, cin, cout = 6, 128, 256
-    n = doc.plan[d].rows
-    x = _rand((n, cin), 1).to(DEV).bfloat16()
-    conv = GraphConv(cin, cout, 7, 7, d - 1).to(DEV)
-    y = conv.run(x, doc.plan[d], stats_idx=doc.plan[d].batch_id, stats_batch=3)
-    st = y._of_stats.cpu()
-    bid = dg.batch_id(d)
-    yf = y.float().cpu().double()
-    s = torch.zeros(3, cout, dtype=torch.float64).index_add_(0, bid, yf)
-    q = torch.zeros(3, cout, dtype=torch.float64).index_add_(0, bid, yf * yf)
-    assert relerr(st[:, :, 0], s) < 2e-3 and relerr(st[:, :, 1], q) < 2e-3
-    gn = DualOctreeGroupNorm(cout).to(DEV)
-    a = gn.run(y, doc.plan[d], 3, act=True).float().cpu()            # uses the fused statistics
-    del y._of_stats
-    b = gn.run(y, doc.plan[d], 3, act=True).float().cpu()            # stand-alone statistics kernel
-    assert relerr(a, b) < 8e-3
