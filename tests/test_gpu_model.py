@@ -153,3 +153,19 @@ def test_graph_and_config1_against_reference_golden():
     conv.weights.data.copy_(torch.from_numpy(g['w']))
     y = conv.to(DEV)(torch.from_numpy(g['x']).to(DEV), doc, 4)
     assert relerr(y.cpu(), torch.from_numpy(g['y'])) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md 8f-3 ("next" row): the dense LR U-Net as a stand-alone stage-1 denoiser
+# (reference graph_unet_lr.py:184-230, called with unet_type="lr" by octfusion_model_union.py:373)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 3e-2)])
+def test_lr_unet_standalone_stage1(uncond, dtype, tol):
+    sd, net = uncond
+    lr_cfg, _ = R.split_cfg(UNCOND)
+    x = _rand((2, 8, 16, 16, 16), 31)
+    ts = torch.tensor([0.7, -1.2])
+    ref = R.lr_forward_dense(x, ts, sd, lr_cfg, as_middle=False)
+    y = net(unet_type='lr', x=x.to(DEV).to(dtype), timesteps=ts.to(DEV))
+    assert y.shape == ref.shape
+    assert relerr(y.float().cpu(), ref) < tol
