@@ -201,12 +201,16 @@ template <int BN>
 struct TcCfg {
   static constexpr int A_BYTES = TC_BM * 128;                       // 16 KB
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN >= 256 ? 4 : BN >= 128 ? 6 : 8;
+  // Two independent rings.  The gathered A tiles need depth: their throughput is (bytes in flight) / (~0.7 us), see
+  // profiles/tc_gather_experiments_r01.md.  The weight tiles stream from L2 by TMA and need only a shallow ring.
+  static constexpr int B_STAGES = BN >= 64 ? 3 : 4;
+  static constexpr int A_STAGES = (192 * 1024 - B_STAGES * B_BYTES) / A_BYTES;      // 6 (BN=256) .. 11
+  static constexpr int STAGES = A_STAGES;                                           // (A ring depth)
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   static constexpr int TAP_BYTES = 0;                               // (tap table is read through L1)
-  static constexpr int AUX_BYTES = 256;                             // mbarriers + tmem slot
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + TAP_BYTES + AUX_BYTES;
+  static constexpr int AUX_BYTES = 512;                             // mbarriers + tmem slot
+  static constexpr int RING_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + TAP_BYTES + AUX_BYTES;
 };
 
 struct TcParams {
@@ -232,13 +236,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t stage_base = smem_base;
-  const uint32_t aux = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAP_BYTES;
-  // aux layout: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem slot
-  const uint32_t bar_full = aux, bar_empty = aux + 8 * Cfg::STAGES;
-  const uint32_t bar_tfull = aux + 16 * Cfg::STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t b_ring = smem_base + Cfg::A_STAGES * Cfg::A_BYTES;
+  const uint32_t aux = smem_base + Cfg::RING_BYTES + Cfg::TAP_BYTES;
+  // aux layout: a_full[16] | a_empty[16] | b_full[4] | b_empty[4] | tmem_full[2] | tmem_empty[2] | tmem slot
+  const uint32_t bar_full = aux, bar_empty = aux + 128;
+  const uint32_t bar_bfull = aux + 256, bar_bempty = aux + 288;
+  const uint32_t bar_tfull = aux + 320, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::TAP_BYTES + 16 * Cfg::STAGES + 32);
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::RING_BYTES + Cfg::TAP_BYTES + 352);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const of_gemm_args& g = p.g;
@@ -246,9 +252,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == TC_EPI_WARPS && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, (TC_PROD_WARPS / TC_GROUPS) * 32 + 1);
+    for (int s = 0; s < Cfg::A_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, (TC_PROD_WARPS / TC_GROUPS) * 32);
       mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < Cfg::B_STAGES; ++s) {
+      mbar_init(bar_bfull + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -341,8 +351,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     // the whole warp walks the pipeline (all lanes wait on the barriers); one elected lane issues
     {
       constexpr uint32_t idesc = make_idesc(BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, bstage = 0;
+      uint32_t phase = 0, bphase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
@@ -350,10 +360,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(bar_bfull + 8 * bstage, bphase);
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint32_t a_addr = stage_base + stage * Cfg::A_BYTES;
+          const uint32_t b_addr = b_ring + bstage * Cfg::B_BYTES;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
@@ -361,11 +372,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
               umma_bf16(d_tmem, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(bar_empty + 8 * stage);            // frees the smem stage when these MMAs retire
+            umma_commit(bar_empty + 8 * stage);            // frees the A stage when these MMAs retire
+            umma_commit(bar_bempty + 8 * bstage);          // ... and the B stage
             if (kb == p.num_kb - 1) umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
           }
           __syncwarp();
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
+          if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; }
         }
       }
     }
@@ -378,17 +391,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t b_addr = stage_base + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+          mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
+          const uint32_t b_addr = b_ring + stage * Cfg::B_BYTES;
           if (elect_one()) {
-            if (p.debug & 2) { mbar_arrive(bar_full + 8 * stage); }
+            if (p.debug & 2) { mbar_arrive(bar_bfull + 8 * stage); }
             else {
-              mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::B_BYTES);
-              bulk_g2s(b_addr, wp + ((int64_t)kb * p.npad + n0) * 128, Cfg::B_BYTES, bar_full + 8 * stage);
+              mbar_arrive_expect_tx(bar_bfull + 8 * stage, Cfg::B_BYTES);
+              bulk_g2s(b_addr, wp + ((int64_t)kb * p.npad + n0) * 128, Cfg::B_BYTES, bar_bfull + 8 * stage);
             }
           }
           __syncwarp();
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == Cfg::B_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -453,10 +466,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 #pragma unroll
         for (int i = 0; i < TC_BM / 8; ++i) t[i] = tnext[i];
         if (kbg + TC_GROUPS < kb_total) fetch_taps(kbg + TC_GROUPS, tnext);
-        const uint32_t stage = kbg % Cfg::STAGES;
-        const uint32_t phase = (kbg / Cfg::STAGES) & 1u;
+        const uint32_t stage = kbg % Cfg::A_STAGES;
+        const uint32_t phase = (kbg / Cfg::A_STAGES) & 1u;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t a_addr = stage_base + stage * Cfg::A_BYTES;
         if (p.debug & 1) {
         } else if (kb < p.cblocks * taps) {
           const int cb = kb / taps;
