@@ -103,26 +103,13 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int batch, int g
       atomicAdd(&bins[(cur_b * groups + g_prev) * 2], a);
       atomicAdd(&bins[(cur_b * groups + g_prev) * 2 + 1], b);
     };
-    // 4 rows per iteration: the four loads are issued before any is consumed (memory-level parallelism)
-    for (int64_t r = r0 + threadIdx.x / tpr; r < r1; r += (int64_t)rp * 4) {
-      int bb[4];
-      float f[4][V];
+    for (int64_t r = r0 + threadIdx.x / tpr; r < r1; r += rp) {
+      const int b = s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample);
+      if (b != cur_b) { flush(); cur_b = b; }
+      float f[V];
+      load_vec<T, V>(src_ptr<T, V>(s, r, cv), f);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t rr = r + (int64_t)u * rp;
-        bb[u] = -2;
-        if (rr < r1) {
-          bb[u] = s.sample_id ? s.sample_id[rr] : (int)(rr / s.rows_per_sample);
-          load_vec<T, V>(src_ptr<T, V>(s, rr, cv), f[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (bb[u] == -2) continue;
-        if (bb[u] != cur_b) { flush(); cur_b = bb[u]; }
-#pragma unroll
-        for (int i = 0; i < V; ++i) { sum[i] += f[u][i]; sq[i] = fmaf(f[u][i], f[u][i], sq[i]); }
-      }
+      for (int i = 0; i < V; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
     }
     flush();
   }
