@@ -124,7 +124,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference, bounded sample
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_steps_per_sec(cfg, batch_full, sample_batch=2, timed=2):
+def cpu_reference_steps_per_sec(cfg, batch_full, sample_batch=1, timed=1):
     from oracle import restate as R
     from oracle.octree_util import octree_from_splits
     from octfusion_b200.synth import synth_splits
@@ -165,7 +165,7 @@ def run_reference(args):
         return
     cfg = config_for(args)
     k = max(1, min(args.steps, 3))
-    base = cpu_reference_steps_per_sec(cfg, args.batch, 2, k)
+    base = cpu_reference_steps_per_sec(cfg, args.batch, 1, k)
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / base['value'],
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -345,7 +345,7 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            cpu = cpu_reference_steps_per_sec(cfg, args.batch, 2, 2)
+            cpu = cpu_reference_steps_per_sec(cfg, args.batch, 1, 1)
         except Exception as e:  # noqa: BLE001
             cpu = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'failed: %r' % (e,)}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
