@@ -166,6 +166,10 @@ int of_embedding_add(const float* table, const int32_t* label, int32_t batch, in
  * refreshed when not NULL. */
 int of_ddim_eps_update(float* x, const float* eps, const float* log_snr, const float* log_snr_next,
                        int64_t n, void* x_act, int32_t act_dtype, void* stream);
+/* "x0" branch of sample_loop (stage 1), models/octfusion_model_union.py:324-344: optional sign() of the
+ * prediction (truncation, :324-325), ancestral mean + sqrt(variance) * noise.  noise == NULL: no noise term. */
+int of_ddpm_x0_update(float* x, float* pred, const float* noise, const float* log_snr, const float* log_snr_next,
+                      int64_t n, int32_t do_sign, void* stream);
 /* dtype conversion / strided row copy: dst[r, 0:c] = src[src_rows ? src_rows[r] : r, 0:c]
  * written to row (dst_rows ? dst_rows[r] : r) */
 int of_copy_rows(const void* src, int64_t lds, int32_t src_dtype, const int32_t* src_rows,

@@ -68,6 +68,7 @@ _PROTOS = {
     'of_learned_sinusoidal': (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     'of_embedding_add': (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     'of_ddim_eps_update': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
+    'of_ddpm_x0_update': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     'of_copy_rows': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp]),
     'of_scan_scratch_bytes': (_i64, [_i64]),
     'of_leaf_rank': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),

@@ -64,6 +64,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (an error the host sees), never a hung GPU.
+// variant for the long waits of the epilogue warps: back off between polls so that the four idle warps do not
+// compete with the producers for issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(200);
+    if (clock64() - t0 > 4000000000ll) {
+      printf("octfusion_b200 gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -279,7 +293,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * BN;
       const int as = it & 1;
-      mbar_wait(bar_tfull + 8 * as, (it >> 1) & 1);
+      if (p.debug & 8192) mbar_wait(bar_tfull + 8 * as, (it >> 1) & 1);
+      else mbar_wait_relaxed(bar_tfull + 8 * as, (it >> 1) & 1);
       tc_fence_after();
       const int m = m0 + r;
       const bool row_ok = m < g.M;

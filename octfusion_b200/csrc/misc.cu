@@ -80,6 +80,24 @@ __global__ void ddim_eps_kernel(float* __restrict__ x, const float* __restrict__
   }
 }
 
+// reference octfusion_model_union.py:324-344 ("x0" branch of sample_loop: stage-1 ancestral update with the
+// truncation trick): pred <- sign(pred) when do_sign; x <- alpha' (x (1-c)/alpha + c pred) + sqrt(sigma'^2 c) noise
+__global__ void ddpm_x0_kernel(float* __restrict__ x, float* __restrict__ pred, const float* __restrict__ noise,
+                               const float* __restrict__ log_snr, const float* __restrict__ log_snr_next, int64_t n,
+                               int do_sign) {
+  const float ls = *log_snr, lsn = *log_snr_next;
+  const float alpha = sqrtf(sigmoid_acc(ls));
+  const float alpha_n = sqrtf(sigmoid_acc(lsn)), sigma_n = sqrtf(sigmoid_acc(-lsn));
+  const float c = -expm1f(ls - lsn);
+  const float sd = sqrtf(sigma_n * sigma_n * c);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float o = pred[i];
+    if (do_sign) { o = o > 0.0f ? 1.0f : (o < 0.0f ? -1.0f : 0.0f); pred[i] = o; }
+    const float mean = alpha_n * (x[i] * (1.0f - c) / alpha + c * o);
+    x[i] = mean + (noise ? sd * noise[i] : 0.0f);
+  }
+}
+
 template <typename TS, typename TD>
 __global__ void copy_rows_kernel(const TS* __restrict__ src, int64_t lds, const int32_t* __restrict__ src_rows,
                                  TD* __restrict__ dst, int64_t ldd, const int32_t* __restrict__ dst_rows,
@@ -297,6 +315,16 @@ extern "C" int of_ddim_eps_update(float* x, const float* eps, const float* log_s
     ddim_eps_kernel<float><<<grid_for(n), 256, 0, st>>>(x, eps, log_snr, log_snr_next, n,
                                                         reinterpret_cast<float*>(x_act));
   OF_LAUNCH_CHECK("of_ddim_eps_update");
+  return OF_OK;
+}
+
+extern "C" int of_ddpm_x0_update(float* x, float* pred, const float* noise, const float* log_snr,
+                                 const float* log_snr_next, int64_t n, int32_t do_sign, void* stream) {
+  OF_REQUIRE(x && pred && log_snr && log_snr_next && n >= 0, "of_ddpm_x0_update: bad arguments");
+  if (n == 0) return OF_OK;
+  ddpm_x0_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, pred, noise, log_snr, log_snr_next,
+                                                                                n, do_sign);
+  OF_LAUNCH_CHECK("of_ddpm_x0_update");
   return OF_OK;
 }
 

@@ -305,6 +305,14 @@ def ddim_eps_update(x, eps, log_snr, log_snr_next, x_act=None):
     return x
 
 
+def ddpm_x0_update(x, pred, log_snr, log_snr_next, noise=None, do_sign=False):
+    """x (fp32, in place) <- ancestral x0-parameterised step; pred is sign()-ed in place when do_sign."""
+    assert x.dtype == torch.float32 and pred.dtype == torch.float32 and x.is_contiguous() and pred.is_contiguous()
+    check(lib.of_ddpm_x0_update(ptr(x), ptr(pred), ptr(noise) if noise is not None else None, ptr(log_snr),
+                                ptr(log_snr_next), x.numel(), 1 if do_sign else 0, stream()), 'of_ddpm_x0_update')
+    return x
+
+
 def exclusive_scan_i32(values, out=None):
     """returns int32 [n+1]: out[i] = sum(values[:i]), out[n] = total."""
     n = values.numel()

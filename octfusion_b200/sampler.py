@@ -100,3 +100,37 @@ def sample_loop(unet_hr, unet_lr, doctree, ddim_steps=200, label=None, noise=Non
     for i in range(ddim_steps):
         st.step(ls[i], ls[i + 1])
     return st.x.clone()
+
+
+TRUNCATED_TIME = 0.7        # reference models/octfusion_model_union.py:39
+
+
+@torch.no_grad()
+def sample_loop_lr(unet_lr, batch_size, z_shape=(8, 16, 16, 16), ddim_steps=200, label=None, seed=0,
+                   truncated_index=TRUNCATED_TIME, act_dtype=torch.bfloat16, device='cuda', noises=None):
+    """Stage 1 ("lr", df_type "x0") of reference sample_loop (octfusion_model_union.py:300-344): the dense 16^3 U-Net
+    with self-conditioning predicts x0; below `truncated_index` the prediction is replaced by its sign and no noise
+    is added.  `noises` (list of steps+1 tensors: initial latent, then one per step) makes the run reproducible for
+    tests; otherwise a seeded device generator is used.  Returns the split signal [B, 8, 16, 16, 16] fp32."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    shape = (batch_size, *z_shape)
+    draw = (lambda i: noises[i].to(dev).float().contiguous()) if noises is not None else \
+        (lambda i: torch.randn(shape, generator=g, device=dev))
+    x = draw(0).clone()
+    x_start = None
+    times = torch.linspace(1.0, 0.0, ddim_steps + 1)
+    ls_dev = torch.zeros(1, device=dev)
+    lsn_dev = torch.zeros(1, device=dev)
+    ts = torch.zeros(batch_size, device=dev)
+    for i in range(ddim_steps):
+        t, t_next = float(times[i]), float(times[i + 1])
+        ls, lsn = beta_linear_log_snr(t), beta_linear_log_snr(t_next)
+        ts.fill_(ls); ls_dev.fill_(ls); lsn_dev.fill_(lsn)
+        xin = x if act_dtype == torch.float32 else x.to(act_dtype)
+        sc = None if x_start is None else (x_start if act_dtype == torch.float32 else x_start.to(act_dtype))
+        pred = unet_lr(x=xin, timesteps=ts, x_self_cond=sc, label=label).float().contiguous()
+        noise = draw(i + 1) if t_next > truncated_index else None
+        ops.ddpm_x0_update(x, pred, ls_dev, lsn_dev, noise=noise, do_sign=(t < truncated_index))
+        x_start = pred
+    return x

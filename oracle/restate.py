@@ -360,6 +360,18 @@ def ddim_eps_update(x, eps, log_snr, log_snr_next):
     return x0 * alpha_n + eps * sigma_n
 
 
+def ddpm_x0_update(x, pred, log_snr, log_snr_next, noise, do_sign):
+    """'x0' branch of sample_loop (octfusion_model_union.py:324-344); returns (x_next, pred_used)."""
+    if do_sign:
+        pred = torch.sign(pred)
+    alpha = torch.sqrt(torch.sigmoid(log_snr))
+    alpha_n, sigma_n = torch.sqrt(torch.sigmoid(log_snr_next)), torch.sqrt(torch.sigmoid(-log_snr_next))
+    c = -torch.expm1(log_snr - log_snr_next)
+    mean = alpha_n * (x * (1 - c) / alpha + c * pred)
+    var = (sigma_n ** 2) * c
+    return mean + torch.sqrt(var) * (noise if noise is not None else torch.zeros_like(x)), pred
+
+
 # ---------------------------------------------------------------------------------------
 # dual-octree graph (dual_octree.py) -- restated GEOMETRICALLY: two graph nodes are joined in
 # direction `dir` when their cells share a face in that direction.  The reference reaches the

@@ -169,3 +169,30 @@ def test_lr_unet_standalone_stage1(uncond, dtype, tol):
     y = net(unet_type='lr', x=x.to(DEV).to(dtype), timesteps=ts.to(DEV))
     assert y.shape == ref.shape
     assert relerr(y.float().cpu(), ref) < tol
+
+
+def test_stage1_sample_loop_x0_branch(uncond):
+    """reference sample_loop 'x0' branch (octfusion_model_union.py:300-344) with explicit noises: self-conditioning,
+    sign() truncation below t=0.7, ancestral noise above."""
+    from octfusion_b200.sampler import sample_loop_lr, beta_linear_log_snr
+    sd, net = uncond
+    lr_cfg, _ = R.split_cfg(UNCOND)
+    steps, b = 4, 2
+    noises = [_rand((b, 8, 16, 16, 16), 100 + i) for i in range(steps + 1)]
+    times = torch.linspace(1.0, 0.0, steps + 1)
+    x, x_start = noises[0].clone(), None
+    for i in range(steps):
+        t, tn = float(times[i]), float(times[i + 1])
+        ls, lsn = torch.tensor(beta_linear_log_snr(t)), torch.tensor(beta_linear_log_snr(tn))
+        xin = x if x_start is None else x
+        inp = torch.cat([x, torch.zeros_like(x) if x_start is None else x_start], 1)
+        pred = R.lr_forward_dense(F_conv_in(inp, sd), torch.full((b,), float(ls)), sd, lr_cfg, as_middle=True)
+        pred = torch.nn.functional.conv3d(pred, sd['unet_lr.out.weight'], sd['unet_lr.out.bias'], padding=1)
+        x, x_start = R.ddpm_x0_update(x, pred, ls, lsn, noises[i + 1] if tn > 0.7 else None, t < 0.7)
+    y = sample_loop_lr(net.unet_lr, b, ddim_steps=steps, act_dtype=torch.float32, noises=noises)
+    assert relerr(y.cpu(), x) < 2e-3
+
+
+def F_conv_in(inp, sd):
+    """input_emb of the stand-alone LR net applied to (x | x_self_cond) (graph_unet_lr.py:198-200)."""
+    return torch.nn.functional.conv3d(inp, sd['unet_lr.input_emb.weight'], sd['unet_lr.input_emb.bias'], padding=1)
