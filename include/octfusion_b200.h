@@ -92,6 +92,9 @@ typedef struct of_gemm_args {
   /* row counts of a0 / a1 (tcgen05 path): > 0 enables the TMA gather4 half of the gather (rows beyond the
    * count are the hardware's zero fill for empty slots); 0 = unknown -> cp.async only                       */
   int32_t rows_a0, rows_a1;
+  /* tcgen05 path with ntype > 0: the node-type K block as a precomputed bf16 [M, 64] tensor (of_graph_type_block,
+   * record-encoded table); NULL = build it inside the kernel for every tile (slow: dependent loads)        */
+  const void* nt_block;
 } of_gemm_args;
 
 /* CUDA-core FFMA path: any shape, fp32-exact accumulation order-insensitive to 1e-6. */
@@ -228,6 +231,9 @@ int of_graph_multi_flags(const int32_t* tap_tab, int64_t slots, int32_t* flags, 
 int of_graph_multi_index(const int32_t* tap_tab, const int32_t* tap_extra, const uint8_t* node_type,
                          int64_t slots, const int32_t* flag_scan, int32_t* tap_tab_ord, int32_t* multi_off,
                          uint64_t* multi_types, void* stream);
+/* out [rows, 64] bf16: column tap*ntype + type = fraction of the slot's neighbours that have that node type */
+int of_graph_type_block(const int32_t* tap_tab, const int32_t* tap_extra, const uint8_t* node_type, int64_t rows,
+                        int32_t taps, int32_t ntype, void* out_bf16, void* stream);
 int of_gather_mean_rows(const void* a0, int64_t lda0, int32_t c0, const void* a1, int64_t lda1, int32_t c1,
                         const int32_t* tap_extra, const int32_t* multi_off, int32_t count, int32_t dtype,
                         void* out, int64_t ldo, void* stream);

@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ('a_multi', _vp), ('ld_multi', _i64),
         ('multi_types', _vp),
         ('rows_a0', _i32), ('rows_a1', _i32),
+        ('nt_block', _vp),
     ]
 
 
@@ -80,6 +81,7 @@ _PROTOS = {
     'of_histogram_i32': (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     'of_graph_multi_flags': (C.c_int, [_vp, _i64, _vp, _vp]),
     'of_graph_multi_index': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'of_graph_type_block': (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     'of_gather_mean_rows': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     'of_graph_edge_count': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'of_graph_edges': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),

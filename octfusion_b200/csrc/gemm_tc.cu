@@ -553,6 +553,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
               else cp_async_16(dst, sp, tv == -1 ? 0u : 16u);
             }
           }
+        } else if (g.nt_block != nullptr) {
+          // node-type block, precomputed per graph (of_graph_type_block): a plain coalesced copy of rows m0..m0+127
+          const __nv_bfloat16* nb = reinterpret_cast<const __nv_bfloat16*>(g.nt_block) + q * 8;
+#pragma unroll
+          for (int i = 0; i < TC_BM / 8; ++i) {
+            const int rr = rbase + 8 * i;
+            const int m = m0 + rr;
+            cp_async_16(a_addr + rr * 128 + ((q ^ (rr & 7)) << 4), m < g.M ? (const void*)(nb + (int64_t)m * 64) : (const void*)nb,
+                        m < g.M ? 16u : 0u);
+          }
         } else {
           // node-type block: column tap*ntype + type holds (#neighbours of that type)/(#neighbours)
           // = mean of the one-hot columns the reference concatenates (modules.py:199-202).
@@ -591,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         // landed (self-incrementing, not counted) + one ordinary release-arrive (counted)
         // one counted arrival per thread: for gathered blocks it fires when this thread's cp.asyncs have landed
         // (cp.async.mbarrier.arrive.noinc); for the node-type block (generic stores + proxy fence) a plain arrive
-        if (kb < p.cblocks * taps && !(p.debug & 1)) cp_async_mbar_arrive_noinc(bar_full + 8 * stage);
+        if ((kb < p.cblocks * taps || g.nt_block != nullptr) && !(p.debug & 1)) cp_async_mbar_arrive_noinc(bar_full + 8 * stage);
         else mbar_arrive(bar_full + 8 * stage);
       }
     }

@@ -344,6 +344,38 @@ __global__ void multi_index_kernel(const int32_t* __restrict__ tab, const int32_
   multi_types[ord] = packed;
 }
 
+// Node-type K block of the tcgen05 GEMM, precomputed once per graph: row m, column tap*ntype + type holds
+// (#neighbours of that type in slot (m, tap)) / (#neighbours) = the mean of the one-hot columns the reference
+// appends to the features (modules.py:199-202) -- a graph constant, so the GEMM streams it like any other A tile
+// instead of chasing tap table -> node_type for every tile.
+__global__ void type_block_kernel(const int32_t* __restrict__ tab, const int32_t* __restrict__ extra,
+                                  const uint8_t* __restrict__ node_type, int64_t rows, int taps, int ntype,
+                                  __nv_bfloat16* __restrict__ out) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  __nv_bfloat16* o = out + m * 64;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(o)[c] = z;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int32_t tv = tab[m * taps + tap];
+    if (tv == -1) continue;
+    unsigned long long packed = 0ull;
+    int n = 1;
+    if (tv >= 0) {
+      packed = 1ull << (8 * node_type[tv]);
+    } else {
+      const int32_t* e = extra + (-(tv + 2));
+      n = e[0];
+      for (int k = 1; k <= n; ++k) packed += 1ull << (8 * node_type[e[k]]);
+    }
+    for (int ty = 0; ty < ntype && ty < 8; ++ty) {
+      const int c = (int)((packed >> (8 * ty)) & 255ull);
+      if (c) o[tap * ntype + ty] = __float2bfloat16_rn((float)c / (float)n);
+    }
+  }
+}
+
 // one thread per (slot, 16-byte chunk): mean over the slot's neighbours, fp32 accumulate
 template <typename T, int V>
 __global__ void gather_mean_rows_kernel(const T* __restrict__ a0, int64_t lda0, int c0, const T* __restrict__ a1,
@@ -410,6 +442,17 @@ extern "C" int of_graph_multi_index(const int32_t* tap_tab, const int32_t* tap_e
       tap_tab, tap_extra, node_type, slots, flag_scan, tap_tab_ord, multi_off,
       reinterpret_cast<unsigned long long*>(multi_types));
   OF_LAUNCH_CHECK("of_graph_multi_index");
+  return OF_OK;
+}
+
+extern "C" int of_graph_type_block(const int32_t* tap_tab, const int32_t* tap_extra, const uint8_t* node_type, int64_t rows,
+                                   int32_t taps, int32_t ntype, void* out_bf16, void* stream) {
+  OF_REQUIRE(tap_tab && node_type && out_bf16 && rows >= 0 && taps > 0 && ntype > 0 && taps * ntype <= 64 && ntype <= 8,
+             "of_graph_type_block: bad arguments");
+  if (rows == 0) return OF_OK;
+  type_block_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tap_tab, tap_extra, node_type, rows, taps, ntype, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  OF_LAUNCH_CHECK("of_graph_type_block");
   return OF_OK;
 }
 

@@ -47,13 +47,23 @@ class TapTable:
     """Neighbour table of the tap-gather GEMM (see include/octfusion_b200.h).
     tab/extra: record encoding (CUDA-core path).  tab_ord/multi_off/multi_types: ordinal encoding of the
     multi-neighbour slots for the tcgen05 path (of_graph_multi_index); n_multi = number of such slots."""
-    __slots__ = ('tab', 'extra', 'taps', 'rows', 'tab_ord', 'multi_off', 'multi_types', 'n_multi')
+    __slots__ = ('tab', 'extra', 'taps', 'rows', 'tab_ord', 'multi_off', 'multi_types', 'n_multi', '_type_blocks')
 
     def __init__(self, tab: torch.Tensor, extra, taps: int):
         assert tab.dtype == torch.int32 and tab.is_contiguous()
         self.tab, self.extra, self.taps = tab, extra, taps
         self.rows = tab.numel() // taps
         self.tab_ord, self.multi_off, self.multi_types, self.n_multi = tab, None, None, 0
+        self._type_blocks = {}
+
+    def type_block(self, ntype, node_type):
+        """bf16 [rows, 64] node-type K block of the tcgen05 GEMM (graph constant, built once per ntype)."""
+        if ntype not in self._type_blocks:
+            out = torch.empty((self.rows, 64), dtype=torch.bfloat16, device=self.tab.device)
+            check(lib.of_graph_type_block(ptr(self.tab), ptr(self.extra), ptr(node_type), self.rows, self.taps, ntype,
+                                          ptr(out), stream()), 'of_graph_type_block')
+            self._type_blocks[ntype] = out
+        return self._type_blocks[ntype]
 
     def index_multi(self, node_type=None):
         """build the ordinal-encoded table (once per graph)."""
@@ -161,6 +171,9 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g.a1, g.lda1, g.c1 = (a1.data_ptr(), a1.stride(0), c1) if a1 is not None else (None, 0, 0)
     g.a_multi, g.ld_multi, g.multi_types = None, 0, None
     g.rows_a0, g.rows_a1 = a0.shape[0], (a1.shape[0] if a1 is not None else 0)
+    g.nt_block = None
+    if use_tc and w.ntype > 0 and tap is not None:
+        g.nt_block = tap.type_block(w.ntype, node_type).data_ptr()
     if tap is not None and use_tc:
         g.tap_tab = tap.tab_ord.data_ptr()
         if tap.n_multi > 0:
