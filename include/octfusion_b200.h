@@ -95,6 +95,9 @@ typedef struct of_gemm_args {
   /* tcgen05 path with ntype > 0: the node-type K block as a precomputed bf16 [M, 64] tensor (of_graph_type_block,
    * record-encoded table); NULL = build it inside the kernel for every tile (slow: dependent loads)        */
   const void* nt_block;
+  /* tcgen05 path: 1 = walk the row tiles from the last to the first.  Alternating the direction from one kernel to
+   * the next lets each kernel start on the rows its producer wrote last, which are still in the 126 MB L2.  */
+  int32_t reverse;
 } of_gemm_args;
 
 /* CUDA-core FFMA path: any shape, fp32-exact accumulation order-insensitive to 1e-6. */
@@ -128,14 +131,14 @@ int of_repack_weight(const float* src, int64_t s_tap, int64_t s_c, int64_t s_n,
  * ------------------------------------------------------------------------------------------ */
 int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                 const int32_t* sample_id, int32_t rows_per_sample, int64_t rows, int32_t batch,
-                int32_t groups, int32_t dtype, double* sums, void* stream);
+                int32_t groups, int32_t dtype, double* sums, int32_t reverse, void* stream);
 int of_gn_finalize(const double* sums, const int32_t* rows_of_sample, int32_t rows_per_sample,
                    const float* gamma, const float* beta, int32_t batch, int32_t channels,
                    int32_t groups, float eps, float count_eps, float* scale, float* shift, void* stream);
 int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                 const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
                 const float* scale, const float* shift, int32_t act, int32_t dtype,
-                void* y, int64_t ldy, void* stream);
+                void* y, int64_t ldy, int32_t reverse, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * QKVAttention.forward   models/networks/modules.py:538-547

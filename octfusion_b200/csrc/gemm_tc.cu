@@ -36,6 +36,12 @@ constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;   // 448
 constexpr int TC_MAX_TAPS = 27;
+#ifndef OF_TC_MMA_SINGLE
+#define OF_TC_MMA_SINGLE 0
+#endif
+#ifndef OF_TC_WARP_ARRIVE
+#define OF_TC_WARP_ARRIVE 0
+#endif
 constexpr int TC_GROUPS = 4;                // producer groups of 2 warps
 
 // ------------------------------------------------------------------------------------------------
@@ -198,6 +204,9 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint3
 __device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -235,7 +244,7 @@ struct TcParams {
   int m_tiles, n_tiles;
   int use_tma;       // 1: half of the row groups of every feature K block are fetched by TMA gather4
   int rows0, rows1;  // row counts of a0 / a1 (TMA out-of-bounds row = zero fill for empty slots)
-  int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA
+  int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA, 32 no tap-table reads, 64 no weight ring at all
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -267,7 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 
   if (warp == TC_EPI_WARPS && lane == 0) {
     for (int s = 0; s < Cfg::A_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, (TC_PROD_WARPS / TC_GROUPS) * 32);
+      mbar_init(bar_full + 8 * s, OF_TC_WARP_ARRIVE ? (TC_PROD_WARPS / TC_GROUPS) : (TC_PROD_WARPS / TC_GROUPS) * 32);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int s = 0; s < Cfg::B_STAGES; ++s) {
@@ -291,7 +300,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     const int r = warp * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / p.n_tiles) * TC_BM, n0 = (tile % p.n_tiles) * BN;
+      const int ptile = g.reverse ? total_tiles - 1 - tile : tile;
+      const int m0 = (ptile / p.n_tiles) * TC_BM, n0 = (ptile % p.n_tiles) * BN;
       const int as = it & 1;
       if (p.debug & 8192) mbar_wait(bar_tfull + 8 * as, (it >> 1) & 1);
       else mbar_wait_relaxed(bar_tfull + 8 * as, (it >> 1) & 1);
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   } else if (warp == TC_EPI_WARPS) {
     // =========================== MMA issuer ===========================
     // the whole warp walks the pipeline (all lanes wait on the barriers); one elected lane issues
-    {
+    if (!OF_TC_MMA_SINGLE || lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
       int stage = 0, bstage = 0;
       uint32_t phase = 0, bphase = 0;
@@ -375,12 +385,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(bar_bfull + 8 * bstage, bphase);
+          if (!(p.debug & 64)) mbar_wait(bar_bfull + 8 * bstage, bphase);
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t a_addr = stage_base + stage * Cfg::A_BYTES;
           const uint32_t b_addr = b_ring + bstage * Cfg::B_BYTES;
-          if (elect_one()) {
+          if (OF_TC_MMA_SINGLE ? true : elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
               if (p.debug & 8) break;
@@ -388,10 +398,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
                         (kb > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(bar_empty + 8 * stage);            // frees the A stage when these MMAs retire
-            umma_commit(bar_bempty + 8 * bstage);          // ... and the B stage
+            if (!(p.debug & 64)) umma_commit(bar_bempty + 8 * bstage);          // ... and the B stage
             if (kb == p.num_kb - 1) umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
           }
-          __syncwarp();
+          if (!OF_TC_MMA_SINGLE) __syncwarp();
           if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
           if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; }
         }
@@ -399,23 +409,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // =========================== weight loader ===========================
-    {
+    if (!OF_TC_MMA_SINGLE || lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const uint8_t* wp = reinterpret_cast<const uint8_t*>(g.w);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles) * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int n0 = ((g.reverse ? total_tiles - 1 - tile : tile) % p.n_tiles) * BN;
+        for (int kb = 0; kb < p.num_kb && !(p.debug & 64); ++kb) {
           mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
           const uint32_t b_addr = b_ring + stage * Cfg::B_BYTES;
-          if (elect_one()) {
+          if (OF_TC_MMA_SINGLE ? true : elect_one()) {
             if (p.debug & 2) { mbar_arrive(bar_bfull + 8 * stage); }
             else {
               mbar_arrive_expect_tx(bar_bfull + 8 * stage, Cfg::B_BYTES);
               bulk_g2s(b_addr, wp + ((int64_t)kb * p.npad + n0) * 128, Cfg::B_BYTES, bar_bfull + 8 * stage);
             }
           }
-          __syncwarp();
+          if (!OF_TC_MMA_SINGLE) __syncwarp();
           if (++stage == Cfg::B_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -443,8 +453,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       const int tile_iter = (int)(kk / (uint32_t)p.num_kb);
       const int kb = (int)(kk - (uint32_t)tile_iter * (uint32_t)p.num_kb);
       const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
-      const int m0 = (tile / p.n_tiles) * TC_BM;
-      if (kb >= feat_kb) return;
+      const int m0 = ((g.reverse ? total_tiles - 1 - tile : tile) / p.n_tiles) * TC_BM;
+      if (kb >= feat_kb || (p.debug & 32)) return;
       const int tap = kb % taps;
       if (tab != nullptr) {
         const uint32_t base = (uint32_t)(m0 + rbase) * (uint32_t)taps + (uint32_t)tap;     // < 2^31 (checked on host)
@@ -470,13 +480,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       }
     };
     int32_t tnext[TC_BM / 8];
+    int prev_stage = -1;
+    (void)prev_stage;
     if ((uint32_t)grp < kb_total) fetch_taps((uint32_t)grp, tnext);
     for (uint32_t kbg = (uint32_t)grp; kbg < kb_total; kbg += TC_GROUPS) {
       {
         const int tile_iter = (int)(kbg / (uint32_t)p.num_kb);
         const int kb = (int)(kbg - (uint32_t)tile_iter * (uint32_t)p.num_kb);
         const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
-        const int m0 = (tile / p.n_tiles) * TC_BM;
+        const int m0 = ((g.reverse ? total_tiles - 1 - tile : tile) / p.n_tiles) * TC_BM;
         int32_t t[TC_BM / 8];
 #pragma unroll
         for (int i = 0; i < TC_BM / 8; ++i) t[i] = tnext[i];
@@ -601,10 +613,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         // landed (self-incrementing, not counted) + one ordinary release-arrive (counted)
         // one counted arrival per thread: for gathered blocks it fires when this thread's cp.asyncs have landed
         // (cp.async.mbarrier.arrive.noinc); for the node-type block (generic stores + proxy fence) a plain arrive
+#if OF_TC_WARP_ARRIVE
+        // one arrival per WARP: commit this block's copies, wait for the PREVIOUS block's (still leaving this
+        // one in flight), make them visible to the async proxy, then one lane signals the previous stage
+        cp_async_commit();
+        if (prev_stage >= 0) {
+          cp_async_wait<1>();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * (uint32_t)prev_stage);
+        }
+        prev_stage = (int)stage;
+#else
         if ((kb < p.cblocks * taps || g.nt_block != nullptr) && !(p.debug & 1)) cp_async_mbar_arrive_noinc(bar_full + 8 * stage);
         else mbar_arrive(bar_full + 8 * stage);
+#endif
       }
     }
+#if OF_TC_WARP_ARRIVE
+    if (prev_stage >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * (uint32_t)prev_stage);
+    }
+#endif
   }
 
   tc_fence_before();

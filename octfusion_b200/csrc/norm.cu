@@ -63,29 +63,47 @@ __device__ __forceinline__ const T* src_ptr(const GnSrc& s, int64_t r, int c) {
                   : reinterpret_cast<const T*>(s.x1) + r * s.ld1 + (c - s.c0);
 }
 
-constexpr int GN_ROWS_PER_CTA = 256;
+constexpr int GN_UNROLL = 4;                               // independent 16-byte loads in flight per thread
+
+// true when all rows [r0, r1) of this CTA belong to one sample (the common case: rows are grouped by sample inside
+// each depth segment of the graph, so only a handful of the 256-row chunks straddle a boundary)
+__device__ __forceinline__ bool chunk_is_uniform(const GnSrc& s, int64_t r0, int64_t r1, int& b0) {
+  if (s.sample_id) {
+    b0 = s.sample_id[r0];
+    bool same = true;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) same = same && (s.sample_id[r] == b0);
+    return __syncthreads_and(same) != 0;
+  }
+  b0 = (int)(r0 / s.rows_per_sample);
+  return (int)((r1 - 1) / s.rows_per_sample) == b0;
+}
 
 // bins: dynamic smem float [batch][groups][2]
 template <typename T, int V>
-__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int batch, int groups, double* sums) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int batch, int groups, int chunk, int reverse, double* sums) {
   extern __shared__ float bins[];
   const int C = s.c0 + s.c1;
   const int cpg = C / groups;
   const int tpr = C / V;                                   // threads per row
-  const int nbins = batch * groups * 2;
+  const int rp = blockDim.x / tpr;                         // rows in flight (>= 1 checked on host)
+  const int64_t r0 = (int64_t)((reverse & 1) ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * chunk;
+  const int64_t r1 = min(r0 + (int64_t)chunk, s.rows);
+  const bool active = (int)threadIdx.x < rp * tpr;
+  const int cv = (threadIdx.x % tpr) * V;
+  // per-thread source: the channel vector lives in x0 or in x1 (fused concat)
+  const T* base = cv < s.c0 ? reinterpret_cast<const T*>(s.x0) + cv : reinterpret_cast<const T*>(s.x1) + (cv - s.c0);
+  const int64_t ld = cv < s.c0 ? s.ld0 : s.ld1;
+  int b0;
+  const bool uniform = chunk_is_uniform(s, r0, r1, b0) && !(reverse & 2);
+  const int nbins = (uniform ? 1 : batch) * groups * 2;
   for (int i = threadIdx.x; i < nbins; i += blockDim.x) bins[i] = 0.0f;
   __syncthreads();
-  const int rp = blockDim.x / tpr;                         // rows in flight (>= 1 checked on host)
-  const int64_t r0 = (int64_t)blockIdx.x * GN_ROWS_PER_CTA;
-  const int64_t r1 = min(r0 + (int64_t)GN_ROWS_PER_CTA, s.rows);
-  if ((int)threadIdx.x < rp * tpr) {
-    const int cv = (threadIdx.x % tpr) * V;
+  if (active) {
     float sum[V], sq[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { sum[i] = 0.0f; sq[i] = 0.0f; }
     int cur_b = -1;
-    auto flush = [&]() {
-      if (cur_b < 0) return;
+    auto flush = [&](int slot) {
       // combine channels that fall in the same group before touching shared memory
       int g_prev = (cv) / cpg;
       float a = 0.0f, b = 0.0f;
@@ -93,30 +111,51 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int batch, int g
       for (int i = 0; i < V; ++i) {
         const int g = (cv + i) / cpg;
         if (g != g_prev) {
-          atomicAdd(&bins[(cur_b * groups + g_prev) * 2], a);
-          atomicAdd(&bins[(cur_b * groups + g_prev) * 2 + 1], b);
+          atomicAdd(&bins[(slot * groups + g_prev) * 2], a);
+          atomicAdd(&bins[(slot * groups + g_prev) * 2 + 1], b);
           a = 0.0f; b = 0.0f; g_prev = g;
         }
         a += sum[i]; b += sq[i];
         sum[i] = 0.0f; sq[i] = 0.0f;
       }
-      atomicAdd(&bins[(cur_b * groups + g_prev) * 2], a);
-      atomicAdd(&bins[(cur_b * groups + g_prev) * 2 + 1], b);
+      atomicAdd(&bins[(slot * groups + g_prev) * 2], a);
+      atomicAdd(&bins[(slot * groups + g_prev) * 2 + 1], b);
     };
-    for (int64_t r = r0 + threadIdx.x / tpr; r < r1; r += rp) {
-      const int b = s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample);
-      if (b != cur_b) { flush(); cur_b = b; }
-      float f[V];
-      load_vec<T, V>(src_ptr<T, V>(s, r, cv), f);
+    int64_t r = r0 + threadIdx.x / tpr;
+    if (uniform) {
+      for (; r + (GN_UNROLL - 1) * rp < r1; r += GN_UNROLL * rp) {
+        float f[GN_UNROLL][V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+        for (int u = 0; u < GN_UNROLL; ++u) load_vec<T, V>(base + (r + u * rp) * ld, f[u]);
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u)
+#pragma unroll
+          for (int i = 0; i < V; ++i) { sum[i] += f[u][i]; sq[i] = fmaf(f[u][i], f[u][i], sq[i]); }
+      }
+      for (; r < r1; r += rp) {
+        float f[V];
+        load_vec<T, V>(base + r * ld, f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+      }
+      flush(0);
+    } else {
+      for (; r < r1; r += rp) {
+        const int b = s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample);
+        if (b != cur_b) { if (cur_b >= 0) flush(cur_b); cur_b = b; }
+        float f[V];
+        load_vec<T, V>(base + r * ld, f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
+      }
+      if (cur_b >= 0) flush(cur_b);
     }
-    flush();
   }
   __syncthreads();
+  double* dst = sums + (uniform ? (int64_t)b0 * groups * 2 : 0);
   for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
     const float v = bins[i];
-    if (v != 0.0f) atomicAdd(&sums[i], (double)v);
+    if (v != 0.0f) atomicAdd(&dst[i], (double)v);
   }
 }
 
@@ -145,29 +184,26 @@ template <> struct FastAct<float> { static __device__ __forceinline__ float silu
 template <> struct FastAct<__nv_bfloat16> { static __device__ __forceinline__ float silu(float v) { return silu_fast(v); } };
 
 // Each thread owns one channel vector and walks down the rows of its CTA's 256-row chunk; the per-(sample,
-// channel) scale/shift pair stays in registers until the sample id changes.
+// channel) scale/shift pair stays in registers until the sample id changes.  Chunks that lie inside one sample
+// (nearly all) take the unrolled path: GN_UNROLL loads in flight, no per-row sample lookup.
 template <typename T, int V>
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, int act, T* y,
-                                                       int64_t ldy) {
+__global__ void __launch_bounds__(256, 5) gn_apply_kernel(GnSrc s, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, int act, int chunk, int reverse,
+                                                          T* y, int64_t ldy) {
   const int C = s.c0 + s.c1;
   const int tpr = C / V;
   const int rp = blockDim.x / tpr;
-  if ((int)threadIdx.x >= rp * tpr) return;
   const int cv = (threadIdx.x % tpr) * V;
-  const int64_t r0 = (int64_t)blockIdx.x * GN_ROWS_PER_CTA;
-  const int64_t r1 = min(r0 + (int64_t)GN_ROWS_PER_CTA, s.rows);
+  const int64_t r0 = (int64_t)((reverse & 1) ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * chunk;
+  const int64_t r1 = min(r0 + (int64_t)chunk, s.rows);
+  int b0;
+  const bool uniform = chunk_is_uniform(s, r0, r1, b0) && !(reverse & 2);
+  if ((int)threadIdx.x >= rp * tpr) return;
+  const T* base = cv < s.c0 ? reinterpret_cast<const T*>(s.x0) + cv : reinterpret_cast<const T*>(s.x1) + (cv - s.c0);
+  const int64_t ld = cv < s.c0 ? s.ld0 : s.ld1;
+  T* yb = y + cv;
   float sc[V], sh[V];
-  int cur_b = -1;
-  for (int64_t r = r0 + threadIdx.x / tpr; r < r1; r += rp) {
-    const int b = s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample);
-    if (b != cur_b) {
-      cur_b = b;
-#pragma unroll
-      for (int i = 0; i < V; ++i) { sc[i] = scale[(int64_t)b * C + cv + i]; sh[i] = shift[(int64_t)b * C + cv + i]; }
-    }
-    float f[V];
-    load_vec<T, V>(src_ptr<T, V>(s, r, cv), f);
+  auto norm_act = [&](float* f) {
     if (act) {
 #pragma unroll
       for (int i = 0; i < V; ++i) f[i] = FastAct<T>::silu(fmaf(f[i], sc[i], sh[i]));
@@ -175,13 +211,57 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, const float* __r
 #pragma unroll
       for (int i = 0; i < V; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
     }
-    store_vec<T, V>(y + r * ldy + cv, f);
+  };
+  int64_t r = r0 + threadIdx.x / tpr;
+  if (uniform) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) { sc[i] = scale[(int64_t)b0 * C + cv + i]; sh[i] = shift[(int64_t)b0 * C + cv + i]; }
+    for (; r + (GN_UNROLL - 1) * rp < r1; r += GN_UNROLL * rp) {
+      float f[GN_UNROLL][V];
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u) load_vec<T, V>(base + (r + u * rp) * ld, f[u]);
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        norm_act(f[u]);
+        store_vec<T, V>(yb + (r + u * rp) * ldy, f[u]);
+      }
+    }
+    for (; r < r1; r += rp) {
+      float f[V];
+      load_vec<T, V>(base + r * ld, f);
+      norm_act(f);
+      store_vec<T, V>(yb + r * ldy, f);
+    }
+    return;
+  }
+  int cur_b = -1;
+  for (; r < r1; r += rp) {
+    const int b = s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample);
+    if (b != cur_b) {
+      cur_b = b;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { sc[i] = scale[(int64_t)b * C + cv + i]; sh[i] = shift[(int64_t)b * C + cv + i]; }
+    }
+    float f[V];
+    load_vec<T, V>(base + r * ld, f);
+    norm_act(f);
+    store_vec<T, V>(yb + r * ldy, f);
   }
 }
 
 static bool vec_ok(const void* p, int64_t ld, int c, int v, int esz) {
   if (p == nullptr) return true;
   return (c % v == 0) && (ld % v == 0) && ((reinterpret_cast<uintptr_t>(p) % (v * esz)) == 0);
+}
+
+// rows per CTA: a fixed number of BYTES per CTA (so that every thread streams enough rows to amortise the
+// prologue/epilogue latency chain), at least 256 rows.  OCTFUSION_GN_CHUNK_KB overrides (experiments).
+static int gn_chunk_rows(int C, int esz) {
+  static int kb = -1;
+  if (kb < 0) { const char* e = getenv("OCTFUSION_GN_CHUNK_KB"); kb = e ? atoi(e) : 64; }
+  int64_t rows = ((int64_t)kb * 1024) / ((int64_t)C * esz);
+  rows = (rows / 256) * 256;
+  return (int)(rows < 256 ? 256 : rows);
 }
 
 static int check_src(const GnSrc& s, const char* who) {
@@ -196,7 +276,7 @@ static int check_src(const GnSrc& s, const char* who) {
 
 extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                            const int32_t* sample_id, int32_t rows_per_sample, int64_t rows, int32_t batch,
-                           int32_t groups, int32_t dtype, double* sums, void* stream) {
+                           int32_t groups, int32_t dtype, double* sums, int32_t reverse, void* stream) {
   using namespace of;
   GnSrc s{x0, ld0, c0, x1, ld1, c1, sample_id, rows_per_sample, rows};
   int rc = check_src(s, "of_gn_stats");
@@ -208,7 +288,8 @@ extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* 
   if (rows == 0) return OF_OK;
   const size_t smem = (size_t)batch * groups * 2 * sizeof(float);
   OF_REQUIRE(smem <= 200 * 1024, "of_gn_stats: batch*groups too large for the shared bins (%zu B)", smem);
-  const int grid = (int)((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA);
+  const int chunk = gn_chunk_rows(C, dtype == OF_F32 ? 4 : 2);
+  const int grid = (int)((rows + chunk - 1) / chunk);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define OF_GN_STATS_LAUNCH(T, V)                                                                      \
   do {                                                                                                \
@@ -218,7 +299,7 @@ extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* 
       cudaFuncSetAttribute(gn_stats_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
       cfg = 200 * 1024;                                                                               \
     }                                                                                                 \
-    gn_stats_kernel<T, V><<<grid, 256, smem, st>>>(s, batch, groups, sums);                           \
+    gn_stats_kernel<T, V><<<grid, 256, smem, st>>>(s, batch, groups, chunk, reverse, sums);                           \
   } while (0)
   if (dtype == OF_F32) {
     if (vec_ok(x0, ld0, c0, 4, 4) && vec_ok(x1, ld1, c1, 4, 4)) OF_GN_STATS_LAUNCH(float, 4);
@@ -249,7 +330,8 @@ extern "C" int of_gn_finalize(const double* sums, const int32_t* rows_of_sample,
 
 extern "C" int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                            const int32_t* sample_id, int32_t rows_per_sample, int64_t rows, const float* scale,
-                           const float* shift, int32_t act, int32_t dtype, void* y, int64_t ldy, void* stream) {
+                           const float* shift, int32_t act, int32_t dtype, void* y, int64_t ldy, int32_t reverse,
+                           void* stream) {
   using namespace of;
   GnSrc s{x0, ld0, c0, x1, ld1, c1, sample_id, rows_per_sample, rows};
   int rc = check_src(s, "of_gn_apply");
@@ -262,8 +344,9 @@ extern "C" int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* 
 #define OF_GN_APPLY_LAUNCH(T, V)                                                              \
   do {                                                                                        \
     OF_REQUIRE(C / V <= 256, "of_gn_apply: C=%d too wide", C);                                \
-    const int grid = (int)((rows + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA);                   \
-    gn_apply_kernel<T, V><<<grid, 256, 0, st>>>(s, scale, shift, act, reinterpret_cast<T*>(y), ldy); \
+    const int chunk = gn_chunk_rows(C, (int)sizeof(T));                                       \
+    const int grid = (int)((rows + chunk - 1) / chunk);                                       \
+    gn_apply_kernel<T, V><<<grid, 256, 0, st>>>(s, scale, shift, act, chunk, reverse, reinterpret_cast<T*>(y), ldy); \
   } while (0)
   if (dtype == OF_F32) {
     if (vec_ok(x0, ld0, c0, 4, 4) && vec_ok(x1, ld1, c1, 4, 4) && vec_ok(y, ldy, C, 4, 4)) OF_GN_APPLY_LAUNCH(float, 4);

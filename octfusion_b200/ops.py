@@ -172,6 +172,7 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g.a_multi, g.ld_multi, g.multi_types = None, 0, None
     g.rows_a0, g.rows_a1 = a0.shape[0], (a1.shape[0] if a1 is not None else 0)
     g.nt_block = None
+    g.reverse = _next_direction() if use_tc else 0
     if use_tc and w.ntype > 0 and tap is not None:
         g.nt_block = tap.type_block(w.ntype, node_type).data_ptr()
     if tap is not None and use_tc:
@@ -239,6 +240,22 @@ def linear_small(x, weight, bias=None, a_silu=False):
     return out
 
 
+_sweep = [0]          # traversal direction of the next streaming kernel (see include/octfusion_b200.h: `reverse`)
+_alternate = [os.environ.get('OCTFUSION_ALTERNATE', '1') != '0']
+
+
+def _next_direction() -> int:
+    """Alternate the row traversal direction from one big kernel to the next, so that each kernel starts on the rows
+    its producer wrote (or read) last -- the part of the tensor that is still resident in L2."""
+    if not _alternate[0]:
+        return 0
+    _sweep[0] ^= 1
+    return _sweep[0]
+
+
+_gn_general = 2 if os.environ.get('OCTFUSION_GN_GENERAL') == '1' else 0      # diagnostics: disable the uniform-chunk path
+
+
 def group_norm(x0, gamma, beta, groups: int, batch: int, *, x1=None, sample_id=None, rows_per_sample=0,
                rows_of_sample=None, eps=1e-5, count_eps=0.0, act=False, out=None):
     """(x0|x1) -> act(groupnorm) with per-sample statistics; stats in fp64, one read + one read/write."""
@@ -252,7 +269,7 @@ def group_norm(x0, gamma, beta, groups: int, batch: int, *, x1=None, sample_id=N
     a1 = (ptr(x1), x1.stride(0), c1) if x1 is not None else (None, 0, 0)
     sid = ptr(sample_id) if sample_id is not None else None
     check(lib.of_gn_stats(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, batch, groups,
-                          dt(x0), ptr(sums), stream()), 'of_gn_stats')
+                          dt(x0), ptr(sums), _next_direction() | _gn_general, stream()), 'of_gn_stats')
     scale = torch.empty((batch, c), dtype=torch.float32, device=dev)
     shift = torch.empty((batch, c), dtype=torch.float32, device=dev)
     check(lib.of_gn_finalize(ptr(sums), ptr(rows_of_sample) if rows_of_sample is not None else None, rows_per_sample,
@@ -261,7 +278,8 @@ def group_norm(x0, gamma, beta, groups: int, batch: int, *, x1=None, sample_id=N
     if out is None:
         out = torch.empty((rows, c), dtype=x0.dtype, device=dev)
     check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, ptr(scale),
-                          ptr(shift), 1 if act else 0, dt(x0), ptr(out), out.stride(0), stream()), 'of_gn_apply')
+                          ptr(shift), 1 if act else 0, dt(x0), ptr(out), out.stride(0), _next_direction() | _gn_general, stream()),
+          'of_gn_apply')
     _trace('group_norm', out)
     return out
 

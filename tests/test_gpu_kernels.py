@@ -258,3 +258,22 @@ def test_graphconv_small_channel_input_padded_to_tc():
     for cin in (3, 8):
         y, ref32, refbf = _graphconv_case(2, 6, cin, 128, 5, torch.bfloat16)
         assert relerr(y, refbf) < 8e-3 and relerr(y, ref32) < 2e-2
+
+
+def test_graph_type_block_matches_edge_lists():
+    """of_graph_type_block == scatter_mean of one_hot(node_type[col]) over (row, dir) (reference modules.py:199-202)."""
+    from tests.util import product_doctree
+    doc = product_doctree(2, 7)
+    for d in range(4, 7):
+        p = doc.plan[d]
+        nt = d - 1
+        blk = p.tap.type_block(nt, p.node_type).float()
+        g = doc.graph[d]
+        row, col, edir = g['edge_idx'][0], g['edge_idx'][1], g['edge_dir']
+        slot = (row * 7 + edir) * nt + p.node_type.long()[col]
+        cnt = torch.zeros(p.rows * 7 * nt, device=DEV).index_add_(0, slot, torch.ones(len(row), device=DEV))
+        tot = torch.zeros(p.rows * 7, device=DEV).index_add_(0, row * 7 + edir, torch.ones(len(row), device=DEV))
+        want = (cnt.view(p.rows, 7, nt) / tot.clamp(min=1).view(p.rows, 7, 1)).reshape(p.rows, 7 * nt)
+        assert blk.shape == (p.rows, 64)
+        assert torch.equal(blk[:, :7 * nt], want.bfloat16().float())
+        assert float(blk[:, 7 * nt:].abs().max()) == 0.0
