@@ -146,6 +146,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors given by their low words; high word = SBO 1024 B (>>4 = 64) | version 1 @46 | SWIZZLE_128B (2) @61
+constexpr uint32_t TC_DESC_HI = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(TC_DESC_HI)
+      : "memory");
+}
 // K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 in [0,14),
 // LBO>>4 in [16,30) (unused for swizzled K-major: 1), SBO>>4 in [32,46) = 1024 B between 8-row
 // groups, version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
@@ -222,12 +235,18 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
 // ------------------------------------------------------------------------------------------------
 template <int BN>
 struct TcCfg {
-  static constexpr int A_BYTES = TC_BM * 128;                       // 16 KB
-  static constexpr int B_BYTES = BN * 128;
+  // One pipeline stage holds KSUB consecutive 64-wide K blocks: the MMA warp then spends its ~0.25 us of waits,
+  // election, descriptor set-up and commits once per KSUB*4 MMAs.  For BN <= 128 four MMAs (<= 256 cycles of tensor
+  // work) are shorter than that loop overhead and the tensor pipe starved (profiles/tc_gather_experiments_r01.md).
+  static constexpr int KSUB = BN <= 128 ? 2 : 1;
+  static constexpr int A_SUB_BYTES = TC_BM * 128;                   // 16 KB: one K block of A
+  static constexpr int B_SUB_BYTES = BN * 128;                      // one K block of B
+  static constexpr int A_BYTES = KSUB * A_SUB_BYTES;
+  static constexpr int B_BYTES = KSUB * B_SUB_BYTES;
   // Two independent rings.  The gathered A tiles need depth: their throughput is (bytes in flight) / (~0.7 us), see
   // profiles/tc_gather_experiments_r01.md.  The weight tiles stream from L2 by TMA and need only a shallow ring.
-  static constexpr int B_STAGES = BN >= 64 ? 3 : 4;
-  static constexpr int A_STAGES = (192 * 1024 - B_STAGES * B_BYTES) / A_BYTES;      // 6 (BN=256) .. 11
+  static constexpr int B_STAGES = KSUB > 1 ? 2 : (BN >= 64 ? 3 : 4);
+  static constexpr int A_STAGES = (192 * 1024 - B_STAGES * B_BYTES) / A_BYTES;      // 6 x 16 KB (BN=256), 4-5 x 32 KB
   static constexpr int STAGES = A_STAGES;                                           // (A ring depth)
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   static constexpr int TAP_BYTES = 0;                               // (tap table is read through L1)
@@ -276,7 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 
   if (warp == TC_EPI_WARPS && lane == 0) {
     for (int s = 0; s < Cfg::A_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, OF_TC_WARP_ARRIVE ? (TC_PROD_WARPS / TC_GROUPS) : (TC_PROD_WARPS / TC_GROUPS) * 32);
+      mbar_init(bar_full + 8 * s, Cfg::KSUB * (TC_PROD_WARPS / TC_GROUPS) * 32);   // every producer thread of the stage's K blocks
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int s = 0; s < Cfg::B_STAGES; ++s) {
@@ -384,22 +403,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         mbar_wait(bar_tempty + 8 * as, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = 0; kb < p.num_kb; kb += Cfg::KSUB) {
           if (!(p.debug & 64)) mbar_wait(bar_bfull + 8 * bstage, bphase);
           mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
+          if (p.debug & 256) tc_fence_after();     // (experiment) not needed: the operands arrive by cp.async / TMA, not tcgen05
           const uint32_t a_addr = stage_base + stage * Cfg::A_BYTES;
           const uint32_t b_addr = b_ring + bstage * Cfg::B_BYTES;
           if (OF_TC_MMA_SINGLE ? true : elect_one()) {
+            // descriptor low words: start address >> 4 (+2 per 32-byte K step), LBO = 1; the high word is constant
+            const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
+            if (!(p.debug & 8)) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              if (p.debug & 8) break;
-              umma_bf16(d_tmem, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+              for (int j = 0; j < Cfg::KSUB; ++j) {
+                if (j > 0 && kb + j >= p.num_kb) break;              // odd K-block count: the last stage is half full
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)
+                  umma_bf16_lo(d_tmem, a_lo + j * (Cfg::A_SUB_BYTES >> 4) + 2 * k, b_lo + j * (Cfg::B_SUB_BYTES >> 4) + 2 * k,
+                               idesc, (kb > 0 || j > 0 || k > 0) ? 1u : 0u);
+              }
             }
             umma_commit(bar_empty + 8 * stage);            // frees the A stage when these MMAs retire
             if (!(p.debug & 64)) umma_commit(bar_bempty + 8 * bstage);          // ... and the B stage
-            if (kb == p.num_kb - 1) umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
+            if (kb + Cfg::KSUB >= p.num_kb) umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
           }
           if (!OF_TC_MMA_SINGLE) __syncwarp();
           if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
@@ -415,14 +441,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       const uint8_t* wp = reinterpret_cast<const uint8_t*>(g.w);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = ((g.reverse ? total_tiles - 1 - tile : tile) % p.n_tiles) * BN;
-        for (int kb = 0; kb < p.num_kb && !(p.debug & 64); ++kb) {
+        for (int kb = 0; kb < p.num_kb && !(p.debug & 64); kb += Cfg::KSUB) {
           mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
           const uint32_t b_addr = b_ring + stage * Cfg::B_BYTES;
           if (OF_TC_MMA_SINGLE ? true : elect_one()) {
             if (p.debug & 2) { mbar_arrive(bar_bfull + 8 * stage); }
             else {
-              mbar_arrive_expect_tx(bar_bfull + 8 * stage, Cfg::B_BYTES);
-              bulk_g2s(b_addr, wp + ((int64_t)kb * p.npad + n0) * 128, Cfg::B_BYTES, bar_bfull + 8 * stage);
+              const int nk = min(Cfg::KSUB, p.num_kb - kb);
+              mbar_arrive_expect_tx(bar_bfull + 8 * stage, (uint32_t)nk * Cfg::B_SUB_BYTES);
+              for (int j = 0; j < nk; ++j)
+                bulk_g2s(b_addr + j * Cfg::B_SUB_BYTES, wp + ((int64_t)(kb + j) * p.npad + n0) * 128, Cfg::B_SUB_BYTES,
+                         bar_bfull + 8 * stage);
             }
           }
           if (!OF_TC_MMA_SINGLE) __syncwarp();
@@ -447,11 +476,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     // The 16 table entries of the NEXT owned block are fetched before waiting for the current stage to be
     // released, which takes the table latency off the stage turnaround.
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t kb_total = (uint32_t)my_tiles * (uint32_t)p.num_kb;
+    // K-block slots of a tile, padded to whole stages (a pad slot carries no data: its owner only arrives)
+    const uint32_t slots = (uint32_t)((p.num_kb + Cfg::KSUB - 1) / Cfg::KSUB * Cfg::KSUB);
+    const uint32_t kb_total = (uint32_t)my_tiles * slots;
     const int feat_kb = p.cblocks * taps;
     auto fetch_taps = [&](uint32_t kk, int32_t* t) {
-      const int tile_iter = (int)(kk / (uint32_t)p.num_kb);
-      const int kb = (int)(kk - (uint32_t)tile_iter * (uint32_t)p.num_kb);
+      const int tile_iter = (int)(kk / slots);
+      const int kb = (int)(kk - (uint32_t)tile_iter * slots);
       const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
       const int m0 = ((g.reverse ? total_tiles - 1 - tile : tile) / p.n_tiles) * TC_BM;
       if (kb >= feat_kb || (p.debug & 32)) return;
@@ -485,19 +516,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     if ((uint32_t)grp < kb_total) fetch_taps((uint32_t)grp, tnext);
     for (uint32_t kbg = (uint32_t)grp; kbg < kb_total; kbg += TC_GROUPS) {
       {
-        const int tile_iter = (int)(kbg / (uint32_t)p.num_kb);
-        const int kb = (int)(kbg - (uint32_t)tile_iter * (uint32_t)p.num_kb);
+        const int tile_iter = (int)(kbg / slots);
+        const int kb = (int)(kbg - (uint32_t)tile_iter * slots);
         const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
         const int m0 = ((g.reverse ? total_tiles - 1 - tile : tile) / p.n_tiles) * TC_BM;
         int32_t t[TC_BM / 8];
 #pragma unroll
         for (int i = 0; i < TC_BM / 8; ++i) t[i] = tnext[i];
         if (kbg + TC_GROUPS < kb_total) fetch_taps(kbg + TC_GROUPS, tnext);
-        const uint32_t stage = kbg % Cfg::A_STAGES;
-        const uint32_t phase = (kbg / Cfg::A_STAGES) & 1u;
+        const uint32_t sg = kbg / Cfg::KSUB;                       // stage counter; this K block is its sub-tile kbg % KSUB
+        const uint32_t stage = sg % Cfg::A_STAGES;
+        const uint32_t phase = (sg / Cfg::A_STAGES) & 1u;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        const uint32_t a_addr = stage_base + stage * Cfg::A_BYTES;
-        if (p.debug & 1) {
+        const uint32_t a_addr = stage_base + stage * Cfg::A_BYTES + (kbg % Cfg::KSUB) * Cfg::A_SUB_BYTES;
+        if ((p.debug & 1) || kb >= p.num_kb) {
         } else if (kb < p.cblocks * taps) {
           const int cb = kb / taps;
           const int ch = cb * TC_BK;
@@ -625,7 +657,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         }
         prev_stage = (int)stage;
 #else
-        if ((kb < p.cblocks * taps || g.nt_block != nullptr) && !(p.debug & 1)) cp_async_mbar_arrive_noinc(bar_full + 8 * stage);
+        if ((kb < p.cblocks * taps || g.nt_block != nullptr) && kb < p.num_kb && !(p.debug & 1)) cp_async_mbar_arrive_noinc(bar_full + 8 * stage);
         else mbar_arrive(bar_full + 8 * stage);
 #endif
       }
