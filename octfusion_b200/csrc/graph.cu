@@ -360,19 +360,18 @@ __global__ void type_block_kernel(const int32_t* __restrict__ tab, const int32_t
   for (int tap = 0; tap < taps; ++tap) {
     const int32_t tv = tab[m * taps + tap];
     if (tv == -1) continue;
-    unsigned long long packed = 0ull;
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};                 // a coarse leaf can face up to 4^k finer cells: plain ints
     int n = 1;
     if (tv >= 0) {
-      packed = 1ull << (8 * node_type[tv]);
+      cnt[node_type[tv] & 7] = 1;
     } else {
       const int32_t* e = extra + (-(tv + 2));
       n = e[0];
-      for (int k = 1; k <= n; ++k) packed += 1ull << (8 * node_type[e[k]]);
+      for (int k = 1; k <= n; ++k) ++cnt[node_type[e[k]] & 7];
     }
-    for (int ty = 0; ty < ntype && ty < 8; ++ty) {
-      const int c = (int)((packed >> (8 * ty)) & 255ull);
-      if (c) o[tap * ntype + ty] = __float2bfloat16_rn((float)c / (float)n);
-    }
+#pragma unroll
+    for (int ty = 0; ty < 8; ++ty)
+      if (ty < ntype && cnt[ty]) o[tap * ntype + ty] = __float2bfloat16_rn((float)cnt[ty] / (float)n);
   }
 }
 

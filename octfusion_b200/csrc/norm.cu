@@ -204,9 +204,15 @@ __global__ void __launch_bounds__(256, 5) gn_apply_kernel(GnSrc s, const float* 
   T* yb = y + cv;
   float sc[V], sh[V];
   auto norm_act = [&](float* f) {
-    if (act) {
+    if (act == 1) {
 #pragma unroll
       for (int i = 0; i < V; ++i) f[i] = FastAct<T>::silu(fmaf(f[i], sc[i], sh[i]));
+    } else if (act == 2) {                                 // exact (erf) GELU = torch.nn.GELU() of the VAE heads
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float v = fmaf(f[i], sc[i], sh[i]);
+        f[i] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < V; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);

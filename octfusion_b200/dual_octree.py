@@ -38,6 +38,14 @@ class _LazyGraph(dict):
         if key in ('edge_idx', 'edge_dir'):
             self._owner._expand_edges(self._d, self)
             return dict.__getitem__(self, key)
+        if key == 'node_mask':                           # dual_octree.py:391-398: over all octree nodes of depths fd..d
+            o = self._owner
+            oc = o.octree
+            parts = [oc.children[k] < 0 for k in range(o.full_depth, self._d)]
+            parts.append(torch.ones(int(o.nnum[self._d]), dtype=torch.bool, device=o.device))
+            v = torch.cat(parts)
+            self[key] = v
+            return v
         if key == 'node_type':
             v = self._owner.plan[self._d].node_type.long()
             self[key] = v

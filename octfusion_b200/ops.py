@@ -256,6 +256,9 @@ def _next_direction() -> int:
 _gn_general = 2 if os.environ.get('OCTFUSION_GN_GENERAL') == '1' else 0      # diagnostics: disable the uniform-chunk path
 
 
+_ACT = {False: 0, None: 0, True: 1, 'silu': 1, 'gelu': 2}
+
+
 def group_norm(x0, gamma, beta, groups: int, batch: int, *, x1=None, sample_id=None, rows_per_sample=0,
                rows_of_sample=None, eps=1e-5, count_eps=0.0, act=False, out=None):
     """(x0|x1) -> act(groupnorm) with per-sample statistics; stats in fp64, one read + one read/write."""
@@ -278,7 +281,7 @@ def group_norm(x0, gamma, beta, groups: int, batch: int, *, x1=None, sample_id=N
     if out is None:
         out = torch.empty((rows, c), dtype=x0.dtype, device=dev)
     check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, ptr(scale),
-                          ptr(shift), 1 if act else 0, dt(x0), ptr(out), out.stride(0), _next_direction() | _gn_general, stream()),
+                          ptr(shift), _ACT[act], dt(x0), ptr(out), out.stride(0), _next_direction() | _gn_general, stream()),
           'of_gn_apply')
     _trace('group_norm', out)
     return out

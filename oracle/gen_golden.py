@@ -93,6 +93,26 @@ def main():
         np.savez_compressed(os.path.join(OUT, 'unet_%s.npz' % name), y=y.numpy(), x_sum=checksum(x),
                             w_sum=sum(checksum(v) for v in sd.values()), batch=batch)
         print(name, 'out absmax', float(y.abs().max()), 'N', d.total_num)
+    # 5. GraphVAE decoder: decode_code(update_octree=True) of the unmodified reference
+    import importlib
+    from tests import util as U
+    gv = importlib.import_module('models.networks.dualoctree_networks.graph_vae')
+    vae = gv.GraphVAE(**U.VAE).eval()
+    sd = U.vae_state_dict()
+    vae.load_state_dict(sd)
+    d_in = ref_doctree(1, 0)
+    code = U.vae_code(d_in.total_num)
+    out = vae.decode_code(code, d_in, update_octree=True)
+    fx = {'code_sum': checksum(code), 'w_sum': sum(checksum(v) for v in sd.values()),
+          'nnum': out['octree_out'].nnum.numpy(), 'nnum_nempty': out['octree_out'].nnum_nempty.numpy()}
+    for d in (6, 7, 8):
+        lg = out['logits'][d]
+        fx['label%d' % d] = np.packbits(lg.argmax(1).numpy().astype(np.uint8))
+        fx['margin%d' % d] = float((lg[:, 0] - lg[:, 1]).abs().min())
+        fx['logit%d' % d] = lg[::16].numpy()
+        fx['reg%d' % d] = out['reg_voxs'][d][::16].numpy()
+    np.savez_compressed(os.path.join(OUT, 'vae_decode.npz'), **fx)
+    print('vae nnum', fx['nnum'].tolist(), 'margins', [fx['margin%d' % d] for d in (6, 7, 8)])
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KB')
 

@@ -382,6 +382,108 @@ _NGH = np.array([[0, 0, 1], [0, 0, -1], [0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 0
 _OPP = np.array([1, 0, 3, 2, 5, 4], np.int64)                      # dual_octree.py:98-100
 
 
+# ---------------------------------------------------------------------------------------
+# GraphVAE decoder: models/networks/dualoctree_networks/graph_vae.py
+# ---------------------------------------------------------------------------------------
+VAE_CHANNELS = [4, 512, 512, 256, 128, 64, 32, 32, 24, 8]      # graph_vae.py:125, channels[depth]
+
+
+def conv1x1_gn(x, doctree, d, sd, prefix, act=None):
+    """Conv1x1Gn / Conv1x1GnGelu / Conv1x1GnGeluSequential (modules.py:343-381): bias-free Linear ->
+    DualOctreeGroupNorm -> optional exact (erf) GELU."""
+    h = x @ sd[prefix + 'conv.linear.weight'].t()
+    h = doctree_group_norm(h, doctree.batch_id(d), doctree.batch_size, sd[prefix + 'gn.weights'], sd[prefix + 'gn.bias'])
+    return F.gelu(h) if act == 'gelu' else h
+
+
+def graph_res_block(x, doctree, d, sd, prefix, n_node_type):
+    """GraphResBlock._forward (modules.py:630-648): GN -> swish -> conv1 -> GN -> swish -> dropout(0) -> conv2,
+    skip = Conv1x1Gn when the channel count changes."""
+    bid, bsz, g = doctree.batch_id(d), doctree.batch_size, doctree.graph[d]
+    h = doctree_group_norm(x, bid, bsz, sd[prefix + 'norm1.weights'], sd[prefix + 'norm1.bias'])
+    h = graph_conv(silu(h), g, sd[prefix + 'conv1.weights'], n_node_type)
+    h = doctree_group_norm(h, bid, bsz, sd[prefix + 'norm2.weights'], sd[prefix + 'norm2.bias'])
+    h = graph_conv(silu(h), g, sd[prefix + 'conv2.weights'], n_node_type)
+    if prefix + 'conv1x1c.conv.linear.weight' in sd:
+        x = conv1x1_gn(x, doctree, d, sd, prefix + 'conv1x1c.')
+    return h + x
+
+
+def graph_res_blocks(x, doctree, d, sd, prefix, num, n_node_type):
+    """GraphResBlocks.forward (modules.py:651-666)."""
+    for i in range(num):
+        x = graph_res_block(x, doctree, d, sd, prefix + 'resblks.%d.' % i, n_node_type)
+    return x
+
+
+def vae_graph_upsample(x, doctree, d, sd, prefix):
+    """dualoctree_networks/modules.py:73-91 (the VAE's GraphUpsample: no graph conv): features of the depth-(d-1)
+    graph -> depth-d graph; Conv1x1GnGelu when the channel count changes."""
+    numd = int(doctree.nnum[d - 1])
+    leaf = doctree.node_child(d - 1) < 0
+    outd = x[x.shape[0] - numd:]
+    out = torch.cat([x[: x.shape[0] - numd], outd[leaf], upsample(outd[~leaf], sd[prefix + 'upsample.weights'])], 0)
+    if prefix + 'conv1x1.conv.linear.weight' in sd:
+        out = conv1x1_gn(out, doctree, d, sd, prefix + 'conv1x1.', 'gelu')
+    return out
+
+
+def vae_graph_downsample(x, doctree, d, sd, prefix):
+    """dualoctree_networks/modules.py:39-66: depth-(d+1) graph features -> depth-d graph (call with the TARGET depth d,
+    as graph_vae.py:155 does)."""
+    numd, lnumd = int(doctree.nnum[d + 1]), int(doctree.lnum[d])
+    leaf = doctree.node_child(d) < 0
+    pooled = downsample(x[x.shape[0] - numd:], sd[prefix + 'downsample.weights'])
+    out = torch.zeros(leaf.shape[0], x.shape[1], dtype=x.dtype)
+    out[leaf] = x[x.shape[0] - lnumd - numd: x.shape[0] - numd]
+    out[~leaf] = pooled
+    out = torch.cat([x[: x.shape[0] - numd - lnumd], out], 0)
+    if prefix + 'conv1x1.conv.linear.weight' in sd:
+        out = conv1x1_gn(out, doctree, d, sd, prefix + 'conv1x1.', 'gelu')
+    return out
+
+
+def _vae_head(h, doctree, d, sd, prefix):
+    """_make_predict_module (graph_vae.py:127-130): Conv1x1GnGeluSequential(C, 32) -> Conv1x1(32, out, bias)."""
+    t = conv1x1_gn(h, doctree, d, sd, prefix + '0.', 'gelu')
+    return t @ sd[prefix + '1.linear.weight'].t() + sd[prefix + '1.linear.bias']
+
+
+def vae_decode(code, doctree, sd, depth_stop, depth_out, resblk_num, update_octree=False, labels=None,
+               make_doctree=None):
+    """GraphVAE.octree_decoder (graph_vae.py:171-223).  `labels` (dict depth -> int tensor) overrides the argmax of
+    the split logits when the octree is grown, so that two implementations can be compared on identical octrees
+    even where a logit pair is a near-tie.  Returns (logits, reg_voxs, octree)."""
+    ch = VAE_CHANNELS
+    make_doctree = make_doctree or DualGraph
+    h = code @ sd['post_KL_conv.linear.weight'].t() + sd['post_KL_conv.linear.bias']
+    h = graph_res_blocks(h, doctree, depth_stop, sd, 'decoder_mid.block_1.', resblk_num, depth_stop - 1)
+    h = graph_res_blocks(h, doctree, depth_stop, sd, 'decoder_mid.block_2.', resblk_num, depth_stop - 1)
+    logits, regs = {}, {}
+    for i, d in enumerate(range(depth_stop, depth_out + 1)):
+        if d > depth_stop:
+            h = vae_graph_upsample(h, doctree, d, sd, 'upsample.%d.' % (i - 1))
+        assert h.shape[1] == ch[d]
+        h = graph_res_blocks(h, doctree, d, sd, 'decoder.%d.' % i, resblk_num, d - 1)
+        logit = _vae_head(h, doctree, d, sd, 'predict.%d.' % i)
+        nnum = int(doctree.nnum[d])
+        logits[d] = logit[logit.shape[0] - nnum:]
+        if update_octree:
+            label = (labels[d] if labels is not None else logits[d].argmax(1)).to(torch.int32)
+            octree = doctree.octree
+            octree.octree_split(label, d)
+            if d < depth_out:
+                octree.octree_grow(d + 1)
+                octree.depth += 1
+            doctree = make_doctree(octree)
+        reg = _vae_head(h, doctree, d, sd, 'regress.%d.' % i)
+        mask = doctree.graph[d]['node_mask']
+        pad = torch.zeros(mask.shape[0], reg.shape[1], dtype=reg.dtype)
+        pad[mask] = reg
+        regs[d] = pad
+    return logits, regs, doctree.octree
+
+
 def _facing_children(direction):
     """child octants (4x+2y+z) of a cell that touch its face looking in `direction`."""
     axis = {0: 0, 1: 0, 2: 1, 3: 1, 4: 2, 5: 2}[int(direction)]      # bit position: z=0,y=1,x=2
@@ -485,9 +587,12 @@ class DualGraph:
             ntype = np.concatenate([np.full(int((child[d] < 0).sum()) if d < D else len(child[d]), d - fd, np.int64)
                                     for d in range(fd, D + 1)])
             bid = np.concatenate([(xyzb[d][3][child[d] < 0] if d < D else xyzb[d][3]) for d in range(fd, D + 1)])
+            # add_node_mask (dual_octree.py:391-398): over ALL octree nodes of depths fd..D, True = graph node
+            nmask = np.concatenate([(child[d] < 0) if d < D else np.ones(len(child[d]), bool) for d in range(fd, D + 1)])
             self.graph[D] = {'edge_idx': torch.from_numpy(np.stack([row[order], col[order]])),
                              'edge_dir': torch.from_numpy(edir[order]),
-                             'node_type': torch.from_numpy(ntype)}
+                             'node_type': torch.from_numpy(ntype),
+                             'node_mask': torch.from_numpy(nmask)}
             self._bid[D] = torch.from_numpy(bid)
         self.total_num = int(self._bid[dep].shape[0])
 
@@ -545,7 +650,7 @@ def seeded_state_dict(shapes: dict, seed: int = 0, dtype=torch.float32):
 
 def _is_norm_key(k: str) -> bool:
     parts = k.split('.')
-    if any('norm' in p for p in parts):
+    if any('norm' in p for p in parts) or (len(parts) >= 2 and parts[-2] == 'gn'):
         return True
     # nn.Sequential(GroupNorm32, SiLU, conv) members: block1.0 / block2.0 / end.0 / <attn seq>.0
     if len(parts) >= 2 and parts[-2] == '0' and parts[-1] in ('weight', 'bias'):

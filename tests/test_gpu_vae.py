@@ -1,0 +1,98 @@
+"""-m gpu parity of the GraphVAE decoder against the oracle and the committed reference
+fixture.  Numerics are compared on IDENTICAL octrees: either the product decodes on a depth-8 octree grown from
+the reference's split labels (update_octree=False), or the oracle re-grows its octree from the labels the product
+chose (update_octree=True) -- a near-tie in a logit pair must not fork the two octrees."""
+import os
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+from tests import util as U
+from tests.util import relerr, oracle_doctree, GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _labels(g):
+    return {d: torch.from_numpy(np.unpackbits(g['label%d' % d])[: int(g['nnum'][d])].astype(np.int64)) for d in (6, 7, 8)}
+
+
+@pytest.fixture(scope='module')
+def setup():
+    g = np.load(os.path.join(GOLDEN, 'vae_decode.npz'))
+    sd = U.vae_state_dict()
+    return g, sd, U.build_vae(sd)
+
+
+def _grown_product_doctree(net, labels):
+    """depth-8 product octree: the depth-6 child octree split with the given labels."""
+    from octfusion_b200 import DualOctree
+    doc6 = U.product_doctree(1, 0)
+    octree = net.create_child_octree(doc6.octree)
+    for d in (6, 7, 8):
+        octree.octree_split(labels[d].to(DEV), d)
+        if d < 8:
+            octree.octree_grow(d + 1)
+            octree.depth += 1
+    return DualOctree(octree)
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
+def test_vae_decode_fixed_octree_matches_reference_fixture(setup, dtype, tol):
+    g, sd, net = setup
+    labels = _labels(g)
+    doc8 = _grown_product_doctree(net, labels)
+    assert doc8.nnum.tolist() == g['nnum'].tolist()
+    code = U.vae_code(doc8.plan[6].rows)
+    out = net.decode_code(code.to(DEV).to(dtype), doc8, update_octree=False)
+    for d in (6, 7, 8):
+        lg = out['logits'][d].float().cpu()
+        assert relerr(lg[::16], torch.from_numpy(g['logit%d' % d])) < tol, d
+        assert relerr(out['reg_voxs'][d].float().cpu()[::16], torch.from_numpy(g['reg%d' % d])) < tol, d
+
+
+def test_vae_decode_grows_the_same_octree_as_the_oracle(setup):
+    g, sd, net = setup
+    doc6 = U.product_doctree(1, 0)
+    code = U.vae_code(doc6.plan[6].rows)
+    out = net.decode_code(code.to(DEV), doc6, update_octree=True)
+    mine = {d: out['logits'][d].float().argmax(1).cpu() for d in (6, 7, 8)}
+    dg, _ = oracle_doctree(1, 0)
+    doc = R.DualGraph(U.oracle_child_octree(dg.octree))
+    logits, regs, octree = R.vae_decode(code, doc, sd, 6, 8, 2, update_octree=True, labels=mine)
+    po = out['octree_out']
+    assert po.nnum.tolist() == octree.nnum.tolist() and po.nnum_nempty.tolist() == octree.nnum_nempty.tolist()
+    for d in (6, 7, 8):
+        assert torch.equal(po.keys[d].cpu(), octree.keys[d]) and torch.equal(po.children[d].cpu(), octree.children[d])
+        assert relerr(out['logits'][d].cpu(), logits[d]) < 1e-3 and relerr(out['reg_voxs'][d].cpu(), regs[d]) < 1e-3
+        # the product's choice may differ from the oracle's own argmax only on near-ties
+        flips = logits[d].argmax(1) != mine[d]
+        assert float((logits[d][:, 0] - logits[d][:, 1]).abs()[flips].max() if flips.any() else 0.0) < 1e-3
+    # and from the reference's labels (fixture) likewise: same octree unless a near-tie flipped
+    ref_labels = _labels(g)
+    if all(torch.equal(ref_labels[d], mine[d]) for d in (6, 7, 8)):
+        assert po.nnum.tolist() == g['nnum'].tolist()
+
+
+def test_vae_graph_of_grown_octree_matches_oracle(setup):
+    """dual graph of the depth-8 octree (coarse leaves face up to 4^4 finer cells): same edge set as the oracle."""
+    g, sd, net = setup
+    labels = _labels(g)
+    doc8 = _grown_product_doctree(net, labels)
+    dg, _ = oracle_doctree(1, 0)
+    octree = U.oracle_child_octree(dg.octree)
+    for d in (6, 7, 8):
+        octree.octree_split(labels[d].int(), d)
+        if d < 8:
+            octree.octree_grow(d + 1)
+            octree.depth += 1
+    ref = R.DualGraph(octree)
+    for d in (7, 8):
+        a = R.edge_set({k: doc8.graph[d][k].cpu() for k in ('edge_idx', 'edge_dir')})
+        b = R.edge_set(ref.graph[d])
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert torch.equal(doc8.graph[d]['node_type'].cpu(), ref.graph[d]['node_type'])
+        assert torch.equal(doc8.graph[d]['node_mask'].cpu(), ref.graph[d]['node_mask'])
+        assert torch.equal(doc8.batch_id(d).cpu(), ref.batch_id(d))

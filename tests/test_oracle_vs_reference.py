@@ -81,3 +81,28 @@ def test_operators_equal_reference(ref):
     t = torch.tensor([9.2, -2.3, 0.1])
     assert relerr(R.timestep_embedding(t, 128), ref.util.timestep_embedding(t, 128)) < 1e-6
     assert abs(float(R.beta_linear_log_snr(torch.tensor(0.3))) - float(ref.util.beta_linear_log_snr(torch.tensor(0.3)))) < 1e-6
+
+
+def test_vae_decode_equals_reference(ref):
+    """GraphVAE: state_dict parity of the product class and decode_code(update_octree=True) of
+    the oracle against the reference on two shapes; the oracle grows its octree with the reference's labels."""
+    import importlib
+    from tests import util as U
+    gv = importlib.import_module('models.networks.dualoctree_networks.graph_vae')
+    net = gv.GraphVAE(**U.VAE).eval()
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == U.vae_shapes()
+    sd = U.vae_state_dict(5)
+    net.load_state_dict(sd)
+    doc = _ref_doctree(ref, 2, 3)
+    code = U.vae_code(doc.total_num, 2)
+    with torch.no_grad():
+        out = net.decode_code(code, doc, update_octree=True)
+    labels = {d: out['logits'][d].argmax(1) for d in (6, 7, 8)}
+    dg, _ = oracle_doctree(2, 3)
+    mine = R.DualGraph(U.oracle_child_octree(dg.octree))
+    logits, regs, octree = R.vae_decode(code, mine, sd, 6, 8, 2, update_octree=True, labels=labels)
+    assert torch.equal(octree.nnum, out['octree_out'].nnum)
+    for d in (6, 7, 8):
+        assert torch.equal(octree.keys[d], out['octree_out'].keys[d])
+        assert torch.equal(octree.children[d], out['octree_out'].children[d])
+        assert relerr(logits[d], out['logits'][d]) < 1e-5 and relerr(regs[d], out['reg_voxs'][d]) < 1e-5

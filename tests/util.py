@@ -53,3 +53,52 @@ def build_product(cfg, sd, device='cuda', stage='hr'):
 
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+# ---- GraphVAE decoder (reference configs/vae_snet_train.yaml) ----
+VAE = dict(depth=8, channel_in=4, nout=4, full_depth=4, depth_stop=6, depth_out=8, resblk_type='basic', bottleneck=4,
+           resblk_num=2, code_channel=16, embed_dim=3)
+VAE_SPLIT_BIAS = 0.15      # keeps the grown octree small enough for the CPU oracle (~15-25 % of the nodes split)
+
+
+def vae_shapes():
+    from octfusion_b200 import graph_vae
+    with torch.device('meta'):
+        net = graph_vae.GraphVAE(**VAE)
+    return {k: tuple(v.shape) for k, v in net.state_dict().items()}
+
+
+def vae_state_dict(seed=3):
+    sd = R.seeded_state_dict(vae_shapes(), seed)
+    for i in range(3):
+        sd['predict.%d.1.linear.bias' % i] = torch.tensor([VAE_SPLIT_BIAS, -VAE_SPLIT_BIAS])
+    return sd
+
+
+def vae_code(rows, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(rows, 3, generator=g)
+
+
+def build_vae(sd, device='cuda'):
+    from octfusion_b200 import graph_vae
+    net = graph_vae.GraphVAE(**VAE)
+    net.load_state_dict(sd)
+    return net.to(device).eval()
+
+
+def oracle_child_octree(octree_in, depth_out=8):
+    """GraphVAE.create_child_octree (graph_vae.py:235-244) on the shim octree."""
+    from oracle.ref_import import ensure_shim
+    ensure_shim()
+    from ocnn.octree import Octree
+    fd, ds = octree_in.full_depth, octree_in.depth
+    out = Octree(depth_out, fd, octree_in.batch_size, 'cpu')
+    for d in range(fd + 1):
+        out.octree_grow_full(d)
+    out.depth = fd
+    for d in range(fd, ds):
+        out.octree_split((octree_in.children[d] >= 0).long(), d)
+        out.octree_grow(d + 1)
+        out.depth += 1
+    return out
