@@ -178,7 +178,11 @@ def test_lr_unet_standalone_stage1(uncond, dtype, tol):
 
 def test_stage1_sample_loop_x0_branch(uncond):
     """reference sample_loop 'x0' branch (octfusion_model_union.py:300-344) with explicit noises: self-conditioning,
-    sign() truncation below t=0.7, ancestral noise above."""
+    sign() truncation below t=0.7, ancestral noise above.  sign() is discontinuous, so the comparison is teacher-forced:
+    at every step the product's network and update kernel run on the ORACLE's state (continuous prediction compared at
+    1e-3; the update -- sign included -- on identical inputs at 1e-5).  The free-running loop must then agree with the
+    oracle everywhere except on the few voxels whose prediction sat within rounding of zero at a sign() step."""
+    from octfusion_b200 import ops
     from octfusion_b200.sampler import sample_loop_lr, beta_linear_log_snr
     sd, net = uncond
     lr_cfg, _ = R.split_cfg(UNCOND)
@@ -189,13 +193,23 @@ def test_stage1_sample_loop_x0_branch(uncond):
     for i in range(steps):
         t, tn = float(times[i]), float(times[i + 1])
         ls, lsn = torch.tensor(beta_linear_log_snr(t)), torch.tensor(beta_linear_log_snr(tn))
-        xin = x if x_start is None else x
         inp = torch.cat([x, torch.zeros_like(x) if x_start is None else x_start], 1)
         pred = R.lr_forward_dense(F_conv_in(inp, sd), torch.full((b,), float(ls)), sd, lr_cfg, as_middle=True)
         pred = torch.nn.functional.conv3d(pred, sd['unet_lr.out.weight'], sd['unet_lr.out.bias'], padding=1)
-        x, x_start = R.ddpm_x0_update(x, pred, ls, lsn, noises[i + 1] if tn > 0.7 else None, t < 0.7)
+        # product network on the oracle's state
+        ts = torch.full((b,), float(ls), device=DEV)
+        mine = net.unet_lr(x=x.to(DEV), timesteps=ts, x_self_cond=None if x_start is None else x_start.to(DEV), label=None)
+        assert relerr(mine.float().cpu(), pred) < 1e-3, i
+        # product update kernel on the oracle's prediction
+        noise = noises[i + 1] if tn > 0.7 else None
+        xp, pp = x.clone().to(DEV).contiguous(), pred.clone().to(DEV).contiguous()
+        ops.ddpm_x0_update(xp, pp, ls.reshape(1).to(DEV), lsn.reshape(1).to(DEV),
+                           noise=None if noise is None else noise.to(DEV).contiguous(), do_sign=(t < 0.7))
+        x, x_start = R.ddpm_x0_update(x, pred, ls, lsn, noise, t < 0.7)
+        assert relerr(xp.cpu(), x) < 1e-5 and relerr(pp.cpu(), x_start) < 1e-5, i
     y = sample_loop_lr(net.unet_lr, b, ddim_steps=steps, act_dtype=torch.float32, noises=noises)
-    assert relerr(y.cpu(), x) < 2e-3
+    off = ((y.cpu() - x).abs() > 2e-3 * float(x.abs().max())).float().mean()
+    assert float(off) < 1e-3, float(off)
 
 
 def F_conv_in(inp, sd):
