@@ -36,12 +36,6 @@ constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;   // 448
 constexpr int TC_MAX_TAPS = 27;
-#ifndef OF_TC_MMA_SINGLE
-#define OF_TC_MMA_SINGLE 0
-#endif
-#ifndef OF_TC_WARP_ARRIVE
-#define OF_TC_WARP_ARRIVE 0
-#endif
 constexpr int TC_GROUPS = 4;                // producer groups of 2 warps
 
 // ------------------------------------------------------------------------------------------------
@@ -214,12 +208,6 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -393,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   } else if (warp == TC_EPI_WARPS) {
     // =========================== MMA issuer ===========================
     // the whole warp walks the pipeline (all lanes wait on the barriers); one elected lane issues
-    if (!OF_TC_MMA_SINGLE || lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc(BN);
       int stage = 0, bstage = 0;
       uint32_t phase = 0, bphase = 0;
@@ -409,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           if (p.debug & 256) tc_fence_after();     // (experiment) not needed: the operands arrive by cp.async / TMA, not tcgen05
           const uint32_t a_addr = stage_base + stage * Cfg::A_BYTES;
           const uint32_t b_addr = b_ring + bstage * Cfg::B_BYTES;
-          if (OF_TC_MMA_SINGLE ? true : elect_one()) {
+          if (elect_one()) {
             // descriptor low words: start address >> 4 (+2 per 32-byte K step), LBO = 1; the high word is constant
             const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
@@ -427,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
             if (!(p.debug & 64)) umma_commit(bar_bempty + 8 * bstage);          // ... and the B stage
             if (kb + Cfg::KSUB >= p.num_kb) umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
           }
-          if (!OF_TC_MMA_SINGLE) __syncwarp();
+          __syncwarp();
           if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
           if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; }
         }
@@ -435,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // =========================== weight loader ===========================
-    if (!OF_TC_MMA_SINGLE || lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint8_t* wp = reinterpret_cast<const uint8_t*>(g.w);
@@ -444,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         for (int kb = 0; kb < p.num_kb && !(p.debug & 64); kb += Cfg::KSUB) {
           mbar_wait(bar_bempty + 8 * stage, phase ^ 1);
           const uint32_t b_addr = b_ring + stage * Cfg::B_BYTES;
-          if (OF_TC_MMA_SINGLE ? true : elect_one()) {
+          if (elect_one()) {
             if (p.debug & 2) { mbar_arrive(bar_bfull + 8 * stage); }
             else {
               const int nk = min(Cfg::KSUB, p.num_kb - kb);
@@ -454,7 +442,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
                          bar_bfull + 8 * stage);
             }
           }
-          if (!OF_TC_MMA_SINGLE) __syncwarp();
+          __syncwarp();
           if (++stage == Cfg::B_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -480,13 +468,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     const uint32_t slots = (uint32_t)((p.num_kb + Cfg::KSUB - 1) / Cfg::KSUB * Cfg::KSUB);
     const uint32_t kb_total = (uint32_t)my_tiles * slots;
     const int feat_kb = p.cblocks * taps;
-    auto fetch_taps = [&](uint32_t kk, int32_t* t) {
-      const int tile_iter = (int)(kk / slots);
-      const int kb = (int)(kk - (uint32_t)tile_iter * slots);
-      const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
-      const int m0 = ((g.reverse ? total_tiles - 1 - tile : tile) / p.n_tiles) * TC_BM;
+    // position of a K-block slot inside this CTA's work: (tile iteration, K block, channel block, tap), advanced
+    // incrementally -- no integer divisions in the producer loop (its instruction stream competes with the MMA warp)
+    struct Pos { int ti, kb, cb, tap; };
+    auto norm = [&](Pos& s) {
+      while (s.kb >= (int)slots) { s.kb -= (int)slots; ++s.ti; s.cb = 0; s.tap = s.kb; }
+      while (s.tap >= taps) { s.tap -= taps; ++s.cb; }
+    };
+    auto tile_m0 = [&](int ti) {
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int pt = g.reverse ? total_tiles - 1 - tile : tile;
+      return (p.n_tiles == 1 ? pt : pt / p.n_tiles) * TC_BM;
+    };
+    auto fetch_taps = [&](const Pos& s, int32_t* t) {
+      const int kb = s.kb;
+      const int m0 = tile_m0(s.ti);
       if (kb >= feat_kb || (p.debug & 32)) return;
-      const int tap = kb % taps;
+      const int tap = s.tap;
       if (tab != nullptr) {
         const uint32_t base = (uint32_t)(m0 + rbase) * (uint32_t)taps + (uint32_t)tap;     // < 2^31 (checked on host)
 #pragma unroll
@@ -511,19 +509,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       }
     };
     int32_t tnext[TC_BM / 8];
-    int prev_stage = -1;
-    (void)prev_stage;
-    if ((uint32_t)grp < kb_total) fetch_taps((uint32_t)grp, tnext);
+    Pos cur{0, grp, 0, grp};
+    norm(cur);
+    if ((uint32_t)grp < kb_total) fetch_taps(cur, tnext);
     for (uint32_t kbg = (uint32_t)grp; kbg < kb_total; kbg += TC_GROUPS) {
       {
-        const int tile_iter = (int)(kbg / slots);
-        const int kb = (int)(kbg - (uint32_t)tile_iter * slots);
-        const int tile = (int)blockIdx.x + tile_iter * (int)gridDim.x;
-        const int m0 = ((g.reverse ? total_tiles - 1 - tile : tile) / p.n_tiles) * TC_BM;
+        const int kb = cur.kb;
+        const int cur_cb = cur.cb;
+        const int m0 = tile_m0(cur.ti);
         int32_t t[TC_BM / 8];
 #pragma unroll
         for (int i = 0; i < TC_BM / 8; ++i) t[i] = tnext[i];
-        if (kbg + TC_GROUPS < kb_total) fetch_taps(kbg + TC_GROUPS, tnext);
+        cur.kb += TC_GROUPS; cur.tap += TC_GROUPS;
+        norm(cur);                                           // now the position of kbg + TC_GROUPS
+        if (kbg + TC_GROUPS < kb_total) fetch_taps(cur, tnext);
         const uint32_t sg = kbg / Cfg::KSUB;                       // stage counter; this K block is its sub-tile kbg % KSUB
         const uint32_t stage = sg % Cfg::A_STAGES;
         const uint32_t phase = (sg / Cfg::A_STAGES) & 1u;
@@ -531,7 +530,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         const uint32_t a_addr = stage_base + stage * Cfg::A_BYTES + (kbg % Cfg::KSUB) * Cfg::A_SUB_BYTES;
         if ((p.debug & 1) || kb >= p.num_kb) {
         } else if (kb < p.cblocks * taps) {
-          const int cb = kb / taps;
+          const int cb = cur_cb;
           const int ch = cb * TC_BK;
           const __nv_bfloat16* src;
           int64_t ld;
@@ -585,16 +584,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           }
           if (!tma_rows) {
             // 16 asynchronous 16-byte global->shared copies back to back (no registers, no waiting):
-            // one neighbour -> its row; none -> zero fill; several -> the pre-averaged row of a_multi
+            // one neighbour -> its row; none -> zero fill; several -> the pre-averaged row of a_multi.
+            // Branch-free address: one select of (base, stride) + one 32x32+64 multiply-add per copy -- the producers'
+            // instruction stream is what the MMA warp competes with for issue slots.
+            const uint32_t dst0 = a_addr + rbase * 128 + ((q ^ (rbase & 7)) << 4);    // (rbase + 8i) & 7 == rbase & 7
+            const uint64_t sbase = reinterpret_cast<uint64_t>(src), mbase = reinterpret_cast<uint64_t>(msrc);
+            const uint32_t ldb = (uint32_t)ld * 2u, ldmb = (uint32_t)g.ld_multi * 2u;  // row strides in bytes
+            // Multi-neighbour slots only occur on rows of coarse leaves (the first rows of the graph): two thirds of
+            // the tiles have none, and then every copy is max / multiply-add / compare / LDGSTS.
+            int32_t lo = t[0];
 #pragma unroll
-            for (int i = 0; i < TC_BM / 8; ++i) {
-              const int rr = rbase + 8 * i;
-              const uint32_t dst = a_addr + rr * 128 + ((q ^ (rr & 7)) << 4);
-              const int32_t tv = t[i];
-              const void* sp = tv >= 0 ? (const void*)(src + (int64_t)tv * ld)
-                                       : (tv == -1 ? (const void*)src : (const void*)(msrc + (int64_t)(-(tv + 2)) * g.ld_multi));
-              if (p.debug & 128) cp_async_16_ca(dst, sp, tv == -1 ? 0u : 16u);
-              else cp_async_16(dst, sp, tv == -1 ? 0u : 16u);
+            for (int i = 1; i < TC_BM / 8; ++i) lo = min(lo, t[i]);
+            if (!__any_sync(0xffffffffu, lo < -1)) {
+#pragma unroll
+              for (int i = 0; i < TC_BM / 8; ++i) {
+                const int32_t tv = t[i];
+                const uint64_t addr = sbase + (uint64_t)(uint32_t)max(tv, 0) * (uint64_t)ldb;
+                cp_async_16(dst0 + i * 1024, reinterpret_cast<const void*>(addr), tv == -1 ? 0u : 16u);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < TC_BM / 8; ++i) {
+                const int32_t tv = t[i];
+                const bool multi = tv < -1;
+                const uint32_t idx = multi ? (uint32_t)(-2 - tv) : (uint32_t)(tv < 0 ? 0 : tv);
+                const uint64_t addr = (multi ? mbase : sbase) + (uint64_t)idx * (uint64_t)(multi ? ldmb : ldb);
+                cp_async_16(dst0 + i * 1024, reinterpret_cast<const void*>(addr), tv == -1 ? 0u : 16u);
+              }
             }
           }
         } else if (g.nt_block != nullptr) {
@@ -645,31 +661,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         // landed (self-incrementing, not counted) + one ordinary release-arrive (counted)
         // one counted arrival per thread: for gathered blocks it fires when this thread's cp.asyncs have landed
         // (cp.async.mbarrier.arrive.noinc); for the node-type block (generic stores + proxy fence) a plain arrive
-#if OF_TC_WARP_ARRIVE
-        // one arrival per WARP: commit this block's copies, wait for the PREVIOUS block's (still leaving this
-        // one in flight), make them visible to the async proxy, then one lane signals the previous stage
-        cp_async_commit();
-        if (prev_stage >= 0) {
-          cp_async_wait<1>();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full + 8 * (uint32_t)prev_stage);
-        }
-        prev_stage = (int)stage;
-#else
         if ((kb < p.cblocks * taps || g.nt_block != nullptr) && kb < p.num_kb && !(p.debug & 1)) cp_async_mbar_arrive_noinc(bar_full + 8 * stage);
         else mbar_arrive(bar_full + 8 * stage);
-#endif
       }
     }
-#if OF_TC_WARP_ARRIVE
-    if (prev_stage >= 0) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * (uint32_t)prev_stage);
-    }
-#endif
   }
 
   tc_fence_before();

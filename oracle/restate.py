@@ -449,6 +449,19 @@ def _vae_head(h, doctree, d, sd, prefix):
     return t @ sd[prefix + '1.linear.weight'].t() + sd[prefix + '1.linear.bias']
 
 
+def vae_encode(data, doctree, sd, depth, depth_stop, resblk_num):
+    """GraphVAE.octree_encoder_step + KL_conv (graph_vae.py:135-168) on given input features `data` [N_depth, 4]:
+    returns the posterior moments (mean | logvar) on the depth_stop graph."""
+    h = graph_conv(data, doctree.graph[depth], sd['conv1.weights'], depth - 1)
+    for i, d in enumerate(range(depth, depth_stop - 1, -1)):
+        h = graph_res_blocks(h, doctree, d, sd, 'encoder.%d.' % i, resblk_num - 1, d - 1)
+        if d > depth_stop:
+            h = vae_graph_downsample(h, doctree, d - 1, sd, 'downsample.%d.' % i)
+    h = doctree_group_norm(h, doctree.batch_id(depth_stop), doctree.batch_size, sd['encoder_norm_out.weights'],
+                           sd['encoder_norm_out.bias'])
+    return F.gelu(h) @ sd['KL_conv.linear.weight'].t() + sd['KL_conv.linear.bias']
+
+
 def vae_decode(code, doctree, sd, depth_stop, depth_out, resblk_num, update_octree=False, labels=None,
                make_doctree=None):
     """GraphVAE.octree_decoder (graph_vae.py:171-223).  `labels` (dict depth -> int tensor) overrides the argmax of

@@ -96,3 +96,16 @@ def test_vae_graph_of_grown_octree_matches_oracle(setup):
         assert torch.equal(doc8.graph[d]['node_type'].cpu(), ref.graph[d]['node_type'])
         assert torch.equal(doc8.graph[d]['node_mask'].cpu(), ref.graph[d]['node_mask'])
         assert torch.equal(doc8.batch_id(d).cpu(), ref.batch_id(d))
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
+def test_vae_encoder_moments_match_oracle(setup, dtype, tol):
+    """encoder half on given input features: conv1 -> res blocks / downsample d8 -> d6 -> norm+GELU -> KL_conv."""
+    g, sd, net = setup
+    labels = _labels(g)
+    doc8 = _grown_product_doctree(net, labels)
+    ref = R.DualGraph(U.oracle_grown_octree(labels))
+    data = torch.randn(ref.total_num, 4, generator=torch.Generator().manual_seed(9))
+    want = R.vae_encode(data, ref, sd, 8, 6, 2)
+    got = net.encode_moments(data.to(DEV).to(dtype), doc8)
+    assert relerr(got.float().cpu(), want) < tol

@@ -106,3 +106,28 @@ def test_vae_decode_equals_reference(ref):
         assert torch.equal(octree.keys[d], out['octree_out'].keys[d])
         assert torch.equal(octree.children[d], out['octree_out'].children[d])
         assert relerr(logits[d], out['logits'][d]) < 1e-5 and relerr(regs[d], out['reg_voxs'][d]) < 1e-5
+
+
+def test_vae_encode_equals_reference(ref):
+    """GraphVAE.octree_encoder_step + KL_conv on given input features (the reference builds them from point clouds
+    with ocnn InputFeature, which is outside the path: `_get_input_feature` is replaced by a seeded tensor)."""
+    import importlib
+    import os
+    import numpy as np
+    from tests import util as U
+    gv = importlib.import_module('models.networks.dualoctree_networks.graph_vae')
+    net = gv.GraphVAE(**U.VAE).eval()
+    sd = U.vae_state_dict()
+    net.load_state_dict(sd)
+    g = np.load(os.path.join(U.GOLDEN, 'vae_decode.npz'))
+    labels = {d: torch.from_numpy(np.unpackbits(g['label%d' % d])[: int(g['nnum'][d])].astype(np.int64)) for d in (6, 7, 8)}
+    octree = U.oracle_grown_octree(labels)
+    doc = ref.dual_octree.DualOctree(octree)
+    doc.post_processing_for_docnn()
+    data = torch.randn(doc.total_num, 4, generator=torch.Generator().manual_seed(9))
+    net._get_input_feature = lambda doctree: data
+    with torch.no_grad():
+        convs = net.octree_encoder_step(octree, doc)
+        want = net.KL_conv(convs[6])
+    mine = R.vae_encode(data, R.DualGraph(octree), sd, 8, 6, 2)
+    assert relerr(mine, want) < 1e-5

@@ -102,3 +102,15 @@ def oracle_child_octree(octree_in, depth_out=8):
         out.octree_grow(d + 1)
         out.depth += 1
     return out
+
+
+def oracle_grown_octree(labels, batch=1, seed=0):
+    """depth-8 shim octree: the depth-6 child octree split with the given per-depth labels."""
+    dg, _ = oracle_doctree(batch, seed)
+    octree = oracle_child_octree(dg.octree)
+    for d in (6, 7, 8):
+        octree.octree_split(labels[d].int(), d)
+        if d < 8:
+            octree.octree_grow(d + 1)
+            octree.depth += 1
+    return octree
