@@ -115,3 +115,32 @@ def octree_from_splits(label_fd, label_fd1, batch_size: int, full_depth: int = 4
     octree.octree_grow(full_depth + 2)
     octree.depth += 1
     return octree
+
+
+def split2octree_small(split, input_depth: int, full_depth: int):
+    """reference utils/util_dualoctree.py:225-250: the stage-1 output `split` [B, 8, 2^fd, 2^fd, 2^fd] (sign = does
+    child k of voxel (x, y, z) exist) -> octree of depth full_depth + 2.  A full-layer voxel is non-empty when any of
+    its 8 children is; the children's own split labels are the 8 channels."""
+    disc = split > 0
+    octree = create_full_octree(input_depth, full_depth, split.shape[0], split.device)
+    x, y, z, b = octree.xyzb(full_depth)
+    octree.octree_split((disc.sum(1) > 0)[b, x, y, z].long(), full_depth)
+    octree.octree_grow(full_depth + 1)
+    octree.depth += 1
+    x, y, z, b = octree.xyzb(full_depth, nempty=True)
+    octree.octree_split(disc[b, :, x, y, z].reshape(-1).long(), full_depth + 1)
+    octree.octree_grow(full_depth + 2)
+    octree.depth += 1
+    return octree
+
+
+def octree2split_small(octree, full_depth: int):
+    """reference utils/util_dualoctree.py:198-211: the inverse -- which children of every full-layer voxel are
+    subdivided, as a [B, 8, 2^fd, 2^fd, 2^fd] tensor in {-1, +1}."""
+    child = octree.children[full_depth + 1]
+    sub = (child >= 0).reshape(-1, 8)                       # per non-empty full-layer node
+    n = 2 ** full_depth
+    out = torch.zeros((octree.batch_size, n, n, n, 8), dtype=torch.float32, device=child.device)
+    x, y, z, b = octree.xyzb(full_depth, nempty=True)
+    out[b, x, y, z] = sub.float()
+    return 2 * out.permute(0, 4, 1, 2, 3).contiguous() - 1

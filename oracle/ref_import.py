@@ -52,3 +52,14 @@ def load():
     ns = types.SimpleNamespace(modules=ref_modules, union=graph_unet_union, hr=graph_unet_hr,
                                lr=graph_unet_lr, util=ldm_diffusion_util, dual_octree=dual_octree)
     return ns
+
+
+def load_util():
+    """reference utils/util_dualoctree.py (split <-> octree helpers of the stage-1 -> stage-2 handoff).  Its module top
+    imports plotting / mesh packages that the handoff functions never touch: stubbed."""
+    load()
+    mpl = _stub('matplotlib', use=lambda *a, **k: None)
+    mpl.pyplot = _stub('matplotlib.pyplot')
+    _stub('plyfile', PlyData=object, PlyElement=object)
+    import importlib
+    return importlib.import_module('utils.util_dualoctree')

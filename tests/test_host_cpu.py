@@ -119,3 +119,21 @@ def test_ragged_all_gather_gloo_world2():
         p.join(60)
     want = torch.arange(15, dtype=torch.float32).reshape(5, 3).tolist()
     assert all(r[1] == want for r in res)
+
+
+def test_split_octree_round_trip_host():
+    """stage-1 -> stage-2 handoff (reference utils/util_dualoctree.py:198-250): split signal -> octree -> split signal
+    reproduces the sign pattern, and the octree built from it again is the same octree (index ops only: any device)."""
+    import torch
+    from octfusion_b200 import octree as P
+    g = torch.Generator().manual_seed(11)
+    s = torch.randn(2, 8, 16, 16, 16, generator=g)
+    s[torch.rand(s.shape, generator=g) < 0.7] = -0.5
+    a = P.split2octree_small(s, 6, 4)
+    assert a.depth == 6 and int(a.nnum[5]) == 8 * int(a.nnum_nempty[4]) and int(a.nnum[6]) == 8 * int(a.nnum_nempty[5])
+    assert int(a.nnum_nempty[5]) == int((s > 0).sum())
+    back = P.octree2split_small(a, 4)
+    assert torch.equal(back, 2.0 * (s > 0).float() - 1.0)
+    b = P.split2octree_small(back, 6, 4)
+    for d in range(4, 7):
+        assert torch.equal(a.keys[d], b.keys[d]) and torch.equal(a.children[d], b.children[d])

@@ -131,3 +131,27 @@ def test_vae_encode_equals_reference(ref):
         want = net.KL_conv(convs[6])
     mine = R.vae_encode(data, R.DualGraph(octree), sd, 8, 6, 2)
     assert relerr(mine, want) < 1e-5
+
+
+def test_split_octree_handoff_equals_reference():
+    """stage-1 -> stage-2 handoff: split2octree_small / octree2split_small of the product
+    (device-agnostic index ops) against the reference's, on a random split signal and its round trip."""
+    from oracle.ref_import import load_util
+    from octfusion_b200 import octree as P
+    util = load_util()
+    g = torch.Generator().manual_seed(4)
+    split = torch.randn(2, 8, 16, 16, 16, generator=g)
+    split[torch.rand(split.shape, generator=g) < 0.6] = -1.0            # sparse, like a surface
+    want = util.split2octree_small(split.clone(), 6, 4)
+    got = P.split2octree_small(split, 6, 4)
+    assert got.depth == want.depth == 6
+    for d in range(4, 7):
+        assert torch.equal(got.keys[d], want.keys[d]) and torch.equal(got.children[d], want.children[d].int())
+    assert got.nnum.tolist() == want.nnum.tolist() and got.nnum_nempty.tolist() == want.nnum_nempty.tolist()
+    back_want = util.octree2split_small(want, 4)
+    back = P.octree2split_small(got, 4)
+    assert torch.equal(back, back_want)
+    # round trip: the octree built from its own split signal is the same octree
+    again = P.split2octree_small(back, 6, 4)
+    for d in range(4, 7):
+        assert torch.equal(again.keys[d], got.keys[d]) and torch.equal(again.children[d], got.children[d])
