@@ -134,3 +134,28 @@ def sample_loop_lr(unet_lr, batch_size, z_shape=(8, 16, 16, 16), ddim_steps=200,
         ops.ddpm_x0_update(x, pred, ls_dev, lsn_dev, noise=noise, do_sign=(t < truncated_index))
         x_start = pred
     return x
+
+
+@torch.no_grad()
+def sample_shapes(stage1_unet_lr, unet_hr, unet_lr, vae, batch_size, ddim_steps=200, label=None, seed=0,
+                  act_dtype=torch.bfloat16, full_depth=4, octree_depth=6, split_small=None, device='cuda'):
+    """The reference's `OctFusionModel.sample` flow without mesh export (octfusion_model_union.py:354-400), every stage
+    on the device: stage-1 dense sampler -> split signal -> octree (`split2octree_small`) -> dual graph -> stage-2
+    latent sampler (CUDA graph per step) -> GraphVAE decoder growing the octree to depth 8.
+    Returns {'split_small', 'octree_small', 'doctree_small', 'samples', 'logits', 'reg_voxs', 'octree_out'}; the
+    reference's NeuralMPU / marching cubes keep consuming `reg_voxs` and `octree_out`."""
+    from .octree import split2octree_small
+    from .dual_octree import DualOctree
+    if split_small is None:
+        split_small = sample_loop_lr(stage1_unet_lr, batch_size, ddim_steps=ddim_steps, label=label, seed=seed,
+                                     act_dtype=act_dtype, device=device)
+    octree_small = split2octree_small(split_small, octree_depth, full_depth)
+    doctree_small = DualOctree(octree_small)
+    doctree_small.post_processing_for_docnn()
+    samples = sample_loop(unet_hr, unet_lr, doctree_small, ddim_steps=ddim_steps, label=label, seed=seed,
+                          act_dtype=act_dtype)
+    out = {'split_small': split_small, 'octree_small': octree_small, 'doctree_small': doctree_small, 'samples': samples}
+    if vae is not None:
+        code = samples if act_dtype == torch.float32 else samples.to(act_dtype)
+        out.update(vae.decode_code(code, doctree_small, update_octree=True))
+    return out

@@ -109,3 +109,29 @@ def test_vae_encoder_moments_match_oracle(setup, dtype, tol):
     want = R.vae_encode(data, ref, sd, 8, 6, 2)
     got = net.encode_moments(data.to(DEV).to(dtype), doc8)
     assert relerr(got.float().cpu(), want) < tol
+
+
+def test_sample_shapes_pipeline_runs_end_to_end(setup):
+    """stage 1 -> split2octree -> dual graph -> stage 2 -> VAE decode (reference OctFusionModel.sample, :354-400) on
+    random weights: a structural test -- every hand-off has the right shape, is finite, and the octree is consistent."""
+    import bench
+    from octfusion_b200 import graph_unet_union
+    from octfusion_b200.sampler import sample_shapes
+    from tests.util import UNCOND
+    g, sd, vae = setup
+    net = bench.randomise_(graph_unet_union.UNet3DModel('hr', **UNCOND), 0).to(DEV).eval()
+    # a plausible stage-1 result instead of 200 steps of an untrained net: the split signal of a synthetic shape
+    from octfusion_b200.octree import octree2split_small
+    split = octree2split_small(U.product_doctree(2, 1).octree, 4)
+    out = sample_shapes(net.unet_lr, net.unet_hr, net.unet_lr, vae, 2, ddim_steps=2, split_small=split)
+    doc = out['doctree_small']
+    assert out['samples'].shape == (doc.total_num, 3) and torch.isfinite(out['samples']).all()
+    o = out['octree_out']
+    assert o.depth == 8 and int(o.nnum[7]) == 8 * int(o.nnum_nempty[6]) and int(o.nnum[8]) == 8 * int(o.nnum_nempty[7])
+    for d in (6, 7, 8):
+        assert out['logits'][d].shape == (int(o.nnum[d]), 2) and torch.isfinite(out['logits'][d].float()).all()
+        assert out['reg_voxs'][d].shape[1] == 4 and torch.isfinite(out['reg_voxs'][d].float()).all()
+    # stage 1 itself (2 steps, untrained): shape + sign() truncation of the last step
+    from octfusion_b200.sampler import sample_loop_lr
+    s = sample_loop_lr(net.unet_lr, 2, ddim_steps=2, act_dtype=torch.float32)
+    assert s.shape == (2, 8, 16, 16, 16) and torch.isfinite(s).all()
