@@ -86,7 +86,9 @@ typedef struct of_gemm_args {
   int32_t dtype;                                 /* activation dtype of a0/a1/resid/out       */
   /* tcgen05 path only: slots with several neighbours read their pre-averaged row.  There tap_tab uses
    * the ORDINAL encoding of of_graph_multi_index: v <= -2 -> row -(v+2) of a_multi (built per input tensor
-   * by of_gather_mean_rows); multi_types[ord] = per-type neighbour counts, 8 bits per type.            */
+   * by of_gather_mean_rows); multi_types[ord] = per-type neighbour counts, 8 bits per type -- only read when
+   * nt_block is NULL, and only exact while a slot has < 256 neighbours of one type (two adaptive levels: <= 16;
+   * deeper octrees such as the VAE's depth 8 must pass nt_block).                                       */
   const void* a_multi; int64_t ld_multi;
   const uint64_t* multi_types;
   /* row counts of a0 / a1 (tcgen05 path): > 0 enables the TMA gather4 half of the gather (rows beyond the
@@ -225,7 +227,7 @@ int of_graph_fill(const of_octree_levels* oct, int32_t D, const int32_t* need_of
                   int32_t* tap_tab, int32_t* tap_extra, uint8_t* node_type, int32_t* batch_id,
                   void* stream);
 /* Multi-neighbour slots (coarse leaf next to a subdivided cell: 4..16 finer neighbours, averaged by
- * scatter_mean, utils/scatter.py:42-66).  of_graph_multi_flags marks them (flags[i] = tap_tab[i] <= -2);
+ * scatter_mean, utils/scatter.py:42-66; up to 4^k for k adaptive levels).  of_graph_multi_flags marks them (flags[i] = tap_tab[i] <= -2);
  * after an exclusive scan of the flags, of_graph_multi_index writes the ordinal-encoded table used by the
  * tcgen05 path (v <= -2 -> -(ordinal+2)), multi_off[ord] = offset of the slot's record in tap_extra, and
  * multi_types[ord] = packed per-type neighbour counts (8 bits per node type).
@@ -234,7 +236,10 @@ int of_graph_multi_flags(const int32_t* tap_tab, int64_t slots, int32_t* flags, 
 int of_graph_multi_index(const int32_t* tap_tab, const int32_t* tap_extra, const uint8_t* node_type,
                          int64_t slots, const int32_t* flag_scan, int32_t* tap_tab_ord, int32_t* multi_off,
                          uint64_t* multi_types, void* stream);
-/* out [rows, 64] bf16: column tap*ntype + type = fraction of the slot's neighbours that have that node type */
+/* Node-type K block of the tcgen05 GEMM, a per-graph constant: out [rows, 64] bf16, column tap*ntype + type =
+ * (#neighbours of that type in slot (row, tap)) / (#neighbours) = the scatter_mean of the one-hot columns that
+ * GraphConv.forward appends to the features (models/networks/modules.py:199-202, 208-210); zero elsewhere.
+ * tap_tab / tap_extra are the RECORD-encoded tables of of_graph_fill.  Requires taps*ntype <= 64, ntype <= 8. */
 int of_graph_type_block(const int32_t* tap_tab, const int32_t* tap_extra, const uint8_t* node_type, int64_t rows,
                         int32_t taps, int32_t ntype, void* out_bf16, void* stream);
 int of_gather_mean_rows(const void* a0, int64_t lda0, int32_t c0, const void* a1, int64_t lda1, int32_t c1,

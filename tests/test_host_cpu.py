@@ -137,3 +137,28 @@ def test_split_octree_round_trip_host():
     b = P.split2octree_small(back, 6, 4)
     for d in range(4, 7):
         assert torch.equal(a.keys[d], b.keys[d]) and torch.equal(a.children[d], b.children[d])
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/octfusion_b200.h compiles as C (gcc, no CUDA headers) and the struct layouts it declares are the ones
+    octfusion_b200/_lib.py hands to ctypes (a field added on one side only would silently shift every pointer)."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    from octfusion_b200 import _lib
+    cc = shutil.which('gcc') or shutil.which('cc')
+    if cc is None:
+        import pytest
+        pytest.skip('no host C compiler')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'abi_check')
+    subprocess.run([cc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(root, 'include'),
+                    os.path.join(root, 'tests', 'c_abi_check.c'), '-o', exe], check=True)
+    out = dict(l.split() for l in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.splitlines())
+    g, o = _lib.GemmArgs, _lib.OctreeLevels
+    assert int(out['sizeof_gemm_args']) == C.sizeof(g)
+    for f in ('tap_tab', 'w', 'out', 'M', 'a_multi', 'nt_block', 'reverse'):
+        assert int(out['off_' + f]) == getattr(g, f).offset, f
+    assert int(out['sizeof_octree_levels']) == C.sizeof(o)
+    assert int(out['off_nnum']) == o.nnum.offset and int(out['off_full_depth']) == o.full_depth.offset
