@@ -11,18 +11,24 @@
 //
 // One persistent CTA per SM, 448 threads, warp-specialised:
 //   warps 0-3   epilogue: tcgen05.ld of the fp32 accumulator, +bias/+emb[batch]/+residual, store
-//   warp  4     MMA issuer (one thread): tcgen05.mma 128 x BN x 16, commits release smem stages
-//   warp  5     weight loader (one thread): cp.async.bulk (TMA 1-D) of pre-swizzled [BN x 64] tiles
-//   warps 6-13  gather producers (4 groups x 2 warps, one K block each in flight):
-//               tap table -> source rows -> (mean) -> swizzled st.shared
-// Pipelines: smem ring (full/empty mbarriers) between {gather, loader} and MMA; two TMEM
-// accumulators (full/empty mbarriers) between MMA and epilogue, so tile i+1 is computed while
-// tile i drains.
+//   warp  4     MMA issuer (whole warp walks the pipeline, elect.sync lane issues): tcgen05.mma 128 x BN x 16,
+//               tcgen05.commit releases the shared-memory stages
+//   warp  5     weight loader: cp.async.bulk (TMA 1-D) of pre-swizzled [BN x 64] tiles
+//   warps 6-13  gather producers (4 groups x 2 warps, each group owns every 4th K block):
+//               tap table -> sixteen 16-byte cp.async (LDGSTS) per thread straight into the swizzled A stage,
+//               completion by cp.async.mbarrier.arrive.noinc; no registers, no waiting.  The producers' address
+//               arithmetic is kept to 4 instructions per copy (it shares issue slots with the MMA warp).
+// Pipelines: two shared-memory rings (A: gathered tiles, deep; B: weight tiles, shallow) with full/empty
+// mbarriers between {producers, loader} and the MMA warp; a stage holds KSUB = 2 K blocks when BN <= 128 so that
+// the MMA warp's per-stage overhead is amortised over 8 MMAs; two TMEM accumulators (full/empty mbarriers)
+// between MMA and epilogue, so tile i+1 is computed while tile i drains.
 //
 // K is consumed as 64-wide blocks ordered (channel block outer, tap inner): the 7 (or 27) taps
-// of one 64-channel slab touch the same few hundred source rows, which then sit in L1.
-// The one-hot node-type columns (modules.py:199-202) become one extra K block of per-slot
-// type fractions; the weights are re-laid once by of_pack_weight_tc.
+// of one 64-channel slab touch the same few hundred source rows, which then sit in L2.
+// The one-hot node-type columns (modules.py:199-202) are one extra K block of per-slot type fractions, read
+// from a per-graph precomputed tensor (of_graph_type_block); slots with several finer neighbours read a
+// pre-averaged row (of_gather_mean_rows); the weights are re-laid once by of_pack_weight_tc.
+// Measurements behind each of these choices: profiles/tc_gather_experiments_r01.md.
 #include "common.cuh"
 #include <stdlib.h>
 #include <string.h>
