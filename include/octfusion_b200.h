@@ -265,6 +265,21 @@ int of_graph_edges(const int32_t* tap_tab, const int32_t* tap_extra, int64_t slo
 int of_dense_tap_table(int32_t mode, int32_t out_res_log2, int32_t batch, int32_t* tap_tab,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * NeuralMPU: the implicit function defined by the GraphVAE decoder's regression values
+ * (reference models/networks/dualoctree_networks/mpu.py:55-140 `octree_linear_pts` + `get_linear_pred`,
+ *  utils/spmm.py `spmm` / `modulated_spmm`).
+ *   pos   [npts, 4] fp32: x, y, z in [-1, 1] and the batch index
+ *   reg   [sum_{d=full_depth..depth} nnum[d], 4] fp32: per octree node (gradient xyz, value) -- `reg_voxs[depth]` of
+ *         GraphVAE.octree_decoder (graph_vae.py:214-221), padded over all nodes
+ *   fval  [npts] fp32 = sum_w (F . [offset, 1]) / (sum_w + 1e-8) over the existing cells around the point at depths
+ *         full_depth..depth (leaves only below `depth`), w = prod(1 - |offset|) * d^2 / 50
+ *   touched [npts] uint8 = 1 when a depth-`depth` cell surrounds the point (the `flgs` mask, mpu.py:139)
+ * Only `children`, `nnum`, `full_depth`, `depth`, `batch` of `oct` are read.
+ * ------------------------------------------------------------------------------------------ */
+int of_mpu_eval(const of_octree_levels* oct, int32_t depth, const float* pos, int64_t npts, const float* reg,
+                float* fval, uint8_t* touched, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,8 @@ depth stay on the device.
 
 The encoder half is constructed (so that checkpoints load strictly) and `octree_encoder_step` is implemented on
 caller-provided input features; building those features from point clouds (`doctree.get_input_feature`, ocnn
-`InputFeature`) and the NeuralMPU SDF evaluation are SURVEY.md 8f rank 4, not part of this path.
+`InputFeature`) is outside this path.  `decode_code(pos=...)` / `output['neural_mpu']` evaluate the decoded implicit
+function with `mpu.NeuralMPU` (csrc/mpu.cu).
 """
 from __future__ import annotations
 import torch
@@ -21,6 +22,7 @@ from . import ops
 from .modules import (GraphConv, DualOctreeGroupNorm, Conv1x1, Upsample, Downsample)
 from .dual_octree import DualOctree
 from .octree import Octree
+from .mpu import NeuralMPU
 
 
 # =================================================================================================
@@ -176,6 +178,7 @@ class GraphVAE(nn.Module):
         self.full_depth, self.depth_stop, self.depth_out = full_depth, depth_stop, depth_out
         self.use_checkpoint, self.resblk_type, self.bottleneck, self.resblk_num = (use_checkpoint, resblk_type,
                                                                                    bottleneck, resblk_num)
+        self.neural_mpu = NeuralMPU(self.full_depth, self.depth_stop, self.depth_out)
         self.resblk_nums = [resblk_num] * 16
         self.channels = [4, 512, 512, 256, 128, 64, 32, 32, 24, 8]          # graph_vae.py:125
         self.dropout = 0.0
@@ -277,8 +280,6 @@ class GraphVAE(nn.Module):
 
     @torch.no_grad()
     def decode_code(self, code, doctree_in, update_octree=True, pos=None):
-        if pos is not None:
-            raise NotImplementedError('NeuralMPU evaluation (reference mpu.py) is SURVEY.md 8f rank 4, not built')
         if update_octree:
             octree_out = self.create_child_octree(doctree_in.octree)
             doctree_out = DualOctree(octree_out)
@@ -286,4 +287,11 @@ class GraphVAE(nn.Module):
         else:
             doctree_out = doctree_in
         out = self.octree_decoder(code, doctree_out, update_octree=update_octree)
-        return {'logits': out[0], 'reg_voxs': out[1], 'octree_out': out[2]}
+        output = {'logits': out[0], 'reg_voxs': out[1], 'octree_out': out[2]}
+        if pos is not None:
+            output['mpus'] = self.neural_mpu(pos, out[1], out[2])
+
+        def _neural_mpu(pos):                              # graph_vae.py:317-322: SDF at arbitrary points, finest depth
+            return self.neural_mpu(pos, out[1], out[2])[self.depth_out][0]
+        output['neural_mpu'] = _neural_mpu
+        return output

@@ -91,6 +91,13 @@ class Octree:
     def xyzb(self, depth, nempty=False):
         return key2xyz(self.key(depth, nempty), depth)
 
+    def search_key(self, query, depth, nempty=False):
+        """index of each query key among the nodes of `depth` (keys are sorted: batch-major Morton order), -1 where
+        absent -- the lookup reference mpu.py:72 relies on."""
+        keys = self.key(depth, nempty)
+        pos = torch.searchsorted(keys, query.long()).clamp(max=keys.numel() - 1)
+        return torch.where(keys[pos] == query.long(), pos, torch.full_like(pos, -1))
+
     def to(self, device):
         device = torch.device(device)
         self.device = device

@@ -383,6 +383,57 @@ _OPP = np.array([1, 0, 3, 2, 5, 4], np.int64)                      # dual_octree
 
 
 # ---------------------------------------------------------------------------------------
+# NeuralMPU: models/networks/dualoctree_networks/mpu.py -- oracle only so far
+# ---------------------------------------------------------------------------------------
+def mpu_eval(pos, reg_voxs, octree, full_depth, depth_stop, depth):
+    """NeuralMPU.__call__ (mpu.py:143-155) restated per query point instead of through sparse matrices.
+    pos [P, 4] = (x, y, z in [-1, 1], batch index).  For every depth d in [full_depth, D] the 8 cells of depth d whose
+    centres surround the point contribute  w * (F . [offset, 1])  with  w = prod(1 - |offset in cells|) * d^2 / 50
+    (mpu.py:88-93), F = reg_voxs[D][node] (4 values: gradient + value), offset rescaled to the [-1, 1] frame (:97);
+    a cell contributes only if it exists, and for d < D only if it is a leaf (:118-121).  Output for D in
+    [depth_stop, depth]: (sum / (sum of weights + 1e-8), point touched by a depth-D cell) (:135-140)."""
+    xyz, bid = pos[:, :3], pos[:, 3].long()
+    p = pos.shape[0]
+    corner = torch.tensor([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)], dtype=pos.dtype)   # mpu.py:37-41
+    nnum_cum = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(octree.nnum, 0)])
+    per_depth = {}
+    for d in range(full_depth, depth + 1):
+        scale = 2 ** d
+        xf = (xyz + 1.0) * (scale / 2.0) - 0.5
+        xi = torch.floor(xf)
+        cells = xi.unsqueeze(1) + corner                                   # [P, 8, 3]
+        off = xf.unsqueeze(1) - cells                                      # in [-1, 1]
+        inb = ((cells > -1) & (cells < scale)).all(-1)
+        c = cells.clamp(0, scale - 1).long()
+        key = _xyz_key_t(c[..., 0], c[..., 1], c[..., 2], bid.unsqueeze(1).expand(-1, 8), d)
+        keys = octree.keys[d]
+        at = torch.searchsorted(keys, key.reshape(-1)).clamp(max=keys.numel() - 1).reshape(p, 8)
+        found = (keys[at] == key) & inb
+        w = (1.0 - off.abs()).prod(-1) * (d ** 2 / 50.0)
+        per_depth[d] = (at, found, w, off * (2.0 / scale))
+    out = {}
+    for D in range(depth_stop, depth + 1):
+        num = torch.zeros(p, dtype=pos.dtype)
+        den = torch.zeros(p, dtype=pos.dtype)
+        for d in range(full_depth, D + 1):
+            at, found, w, off = per_depth[d]
+            use = found if d == D else found & (octree.children[d][at] < 0)
+            f = reg_voxs[D][at + int(nnum_cum[d] - nnum_cum[full_depth])]   # [P, 8, 4]
+            val = (f[..., :3] * off).sum(-1) + f[..., 3]
+            num = num + torch.where(use, w * val, torch.zeros_like(w)).sum(1)
+            den = den + torch.where(use, w, torch.zeros_like(w)).sum(1)
+        out[D] = (num / (den + 1e-8), per_depth[D][1].any(1))
+    return out
+
+
+def _xyz_key_t(x, y, z, b, depth):
+    k = torch.zeros_like(x)
+    for i in range(depth):
+        k = k | (((x >> i) & 1) << (3 * i + 2)) | (((y >> i) & 1) << (3 * i + 1)) | (((z >> i) & 1) << (3 * i))
+    return k | (b << 48)
+
+
+# ---------------------------------------------------------------------------------------
 # GraphVAE decoder (SURVEY.md 8f rank 1): models/networks/dualoctree_networks/graph_vae.py
 # ---------------------------------------------------------------------------------------
 VAE_CHANNELS = [4, 512, 512, 256, 128, 64, 32, 32, 24, 8]      # graph_vae.py:125, channels[depth]

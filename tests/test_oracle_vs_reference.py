@@ -155,3 +155,33 @@ def test_split_octree_handoff_equals_reference():
     again = P.split2octree_small(back, 6, 4)
     for d in range(4, 7):
         assert torch.equal(again.keys[d], got.keys[d]) and torch.equal(again.children[d], got.children[d])
+
+
+def test_neural_mpu_equals_reference(ref, monkeypatch):
+    """NeuralMPU (oracle only): per-point restatement against reference mpu.py on the octree and
+    regression values of the VAE fixture case.  mpu.py:136 hard-codes `.cuda()`; on this CPU-only host it is patched
+    to the identity."""
+    import importlib
+    import os
+    import numpy as np
+    from tests import util as U
+    mpu = importlib.import_module('models.networks.dualoctree_networks.mpu')
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    g = np.load(os.path.join(U.GOLDEN, 'vae_decode.npz'))
+    labels = {d: torch.from_numpy(np.unpackbits(g['label%d' % d])[: int(g['nnum'][d])].astype(np.int64)) for d in (6, 7, 8)}
+    octree = U.oracle_grown_octree(labels)
+    gen = torch.Generator().manual_seed(21)
+    ntot = {d: int(octree.nnum[4:d + 1].sum()) for d in (6, 7, 8)}
+    reg = {d: torch.randn(ntot[d], 4, generator=gen) for d in (6, 7, 8)}
+    # query points: near occupied depth-8 cells (so that every depth contributes) plus uniform ones (mostly coarse)
+    x, y, z, b = octree.xyzb(8)
+    pick = torch.randperm(x.numel(), generator=gen)[:4000]
+    near = (torch.stack([x, y, z], 1)[pick].float() + torch.rand(4000, 3, generator=gen)) / 128.0 - 1.0
+    uni = torch.rand(4000, 3, generator=gen) * 2 - 1
+    pos = torch.cat([torch.cat([near, uni]), torch.zeros(8000, 1)], 1)
+    want = mpu.NeuralMPU(4, 6, 8)(pos, reg, octree)
+    mine = R.mpu_eval(pos, reg, octree, 4, 6, 8)
+    for d in (6, 7, 8):
+        assert torch.equal(mine[d][1], want[d][1])
+        assert relerr(mine[d][0], want[d][0]) < 1e-5, d
+    assert bool(want[8][1].any()) and not bool(want[8][1].all())
