@@ -32,6 +32,41 @@ def seeded_inputs(n, c, seed):
     return torch.randn(n, c, generator=g)
 
 
+def mpu_inputs(octree, npts=2000, seed=21):
+    """seeded query points (half near occupied depth-8 cells, half uniform) and regression values for mpu tests."""
+    gen = torch.Generator().manual_seed(seed)
+    reg = {d: torch.randn(int(octree.nnum[4:d + 1].sum()), 4, generator=gen) for d in (6, 7, 8)}
+    x, y, z, b = octree.xyzb(8)
+    pick = torch.randperm(x.numel(), generator=gen)[:npts]
+    near = (torch.stack([x, y, z], 1)[pick].float() + torch.rand(npts, 3, generator=gen)) / 128.0 - 1.0
+    uni = torch.rand(npts, 3, generator=gen) * 2 - 1
+    pos = torch.cat([torch.cat([near, uni]), torch.zeros(2 * npts, 1)], 1)
+    return pos, reg
+
+
+def mpu_fixture():
+    """outputs of the unmodified reference NeuralMPU (mpu.py:143-155; its hard-coded `.cuda()` patched to identity)."""
+    import importlib
+    from tests import util as U
+    ref_import.load()
+    mpu = importlib.import_module('models.networks.dualoctree_networks.mpu')
+    g = np.load(os.path.join(OUT, 'vae_decode.npz'))
+    labels = {d: torch.from_numpy(np.unpackbits(g['label%d' % d])[: int(g['nnum'][d])].astype(np.int64)) for d in (6, 7, 8)}
+    octree = U.oracle_grown_octree(labels)
+    pos, reg = mpu_inputs(octree)
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        out = mpu.NeuralMPU(4, 6, 8)(pos, reg, octree)
+    finally:
+        torch.Tensor.cuda = orig
+    fx = {'pos_sum': checksum(pos), 'reg_sum': sum(checksum(v) for v in reg.values())}
+    for d in (6, 7, 8):
+        fx['fval%d' % d] = out[d][0].numpy()
+        fx['flag%d' % d] = np.packbits(out[d][1].numpy())
+    return fx
+
+
 def main():
     ref = ref_import.load()
     os.makedirs(OUT, exist_ok=True)
@@ -113,6 +148,9 @@ def main():
         fx['reg%d' % d] = out['reg_voxs'][d][::16].numpy()
     np.savez_compressed(os.path.join(OUT, 'vae_decode.npz'), **fx)
     print('vae nnum', fx['nnum'].tolist(), 'margins', [fx['margin%d' % d] for d in (6, 7, 8)])
+    # 6. NeuralMPU on the octree grown above, random per-node regression values
+    fx = mpu_fixture()
+    np.savez_compressed(os.path.join(OUT, 'mpu_eval.npz'), **fx)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KB')
 
