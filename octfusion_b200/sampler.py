@@ -105,6 +105,18 @@ def sample_loop(unet_hr, unet_lr, doctree, ddim_steps=200, label=None, noise=Non
 TRUNCATED_TIME = 0.7        # reference models/octfusion_model_union.py:39
 
 
+def truncation_flags(ddim_steps: int, truncated_index: float = TRUNCATED_TIME):
+    """Per step (do_sign, add_noise) of the stage-1 loop, decided exactly as the reference does: on the float32 time
+    tensors (`t[0] < truncated_index`, octfusion_model_union.py:324; `t_next > truncated_index`, :339).  torch casts
+    the Python scalar to the tensor's dtype, so 0.7 is compared as float32(0.7) = 0.699999988, which
+    linspace(1, 0, steps+1) hits exactly for steps = 10, 50, 100, 200, 1000 -- a float64 compare would apply sign()
+    one step early there."""
+    times = torch.linspace(1.0, 0.0, ddim_steps + 1, dtype=torch.float32)
+    do_sign = [bool(times[i] < truncated_index) for i in range(ddim_steps)]
+    add_noise = [bool(times[i + 1] > truncated_index) for i in range(ddim_steps)]
+    return do_sign, add_noise
+
+
 @torch.no_grad()
 def sample_loop_lr(unet_lr, batch_size, z_shape=(8, 16, 16, 16), ddim_steps=200, label=None, seed=0,
                    truncated_index=TRUNCATED_TIME, act_dtype=torch.bfloat16, device='cuda', noises=None):
@@ -120,6 +132,7 @@ def sample_loop_lr(unet_lr, batch_size, z_shape=(8, 16, 16, 16), ddim_steps=200,
     x = draw(0).clone()
     x_start = None
     times = torch.linspace(1.0, 0.0, ddim_steps + 1)
+    do_sign, add_noise = truncation_flags(ddim_steps, truncated_index)
     ls_dev = torch.zeros(1, device=dev)
     lsn_dev = torch.zeros(1, device=dev)
     ts = torch.zeros(batch_size, device=dev)
@@ -130,8 +143,8 @@ def sample_loop_lr(unet_lr, batch_size, z_shape=(8, 16, 16, 16), ddim_steps=200,
         xin = x if act_dtype == torch.float32 else x.to(act_dtype)
         sc = None if x_start is None else (x_start if act_dtype == torch.float32 else x_start.to(act_dtype))
         pred = unet_lr(x=xin, timesteps=ts, x_self_cond=sc, label=label).float().contiguous()
-        noise = draw(i + 1) if t_next > truncated_index else None
-        ops.ddpm_x0_update(x, pred, ls_dev, lsn_dev, noise=noise, do_sign=(t < truncated_index))
+        noise = draw(i + 1) if add_noise[i] else None
+        ops.ddpm_x0_update(x, pred, ls_dev, lsn_dev, noise=noise, do_sign=do_sign[i])
         x_start = pred
     return x
 

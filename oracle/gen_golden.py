@@ -67,16 +67,46 @@ def mpu_fixture():
     return fx
 
 
+# round-2 additions to UNET_CASES (tests/util.py): the benchmarked 8-channel config and the cond config at the shard
+# size of BASELINE.json configs[4] (B = 4 per GPU)
+from tests.util import UNET_CASES, UNET_TS, UNET_LABEL           # noqa: E402
+
+
+def _ref_doctree(ref, batch, seed):
+    l4, l5 = synth_splits(batch, seed)
+    doc = ref.dual_octree.DualOctree(octree_from_splits(l4, l5, batch))
+    doc.post_processing_for_docnn()
+    return doc
+
+
+def unet_fixture(ref, name):
+    """full HR forward of the unmodified reference on seeded inputs -> tests/golden/unet_<name>.npz"""
+    cfg, batch, cc = UNET_CASES[name]
+    net = ref.union.UNet3DModel('hr', **cfg).eval()
+    sd = R.seeded_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 1)
+    net.load_state_dict(sd)
+    d = _ref_doctree(ref, batch, 0)
+    x = seeded_inputs(d.total_num, cc, 7)
+    ts = torch.tensor(UNET_TS)[:batch]
+    label = torch.tensor(UNET_LABEL)[:batch] if cfg.get('num_classes') else None
+    y = net(unet_type='hr', x=x, doctree=d, timesteps=ts, unet_lr=net.unet_lr, label=label)
+    np.savez_compressed(os.path.join(OUT, 'unet_%s.npz' % name), y=y.numpy(), x_sum=checksum(x),
+                        w_sum=sum(checksum(v) for v in sd.values()), batch=batch)
+    print(name, 'out absmax', float(y.abs().max()), 'N', d.total_num)
+
+
 def main():
     ref = ref_import.load()
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
+    only = [a for a in sys.argv[1:] if a in UNET_CASES]
+    if only:                                   # python -m oracle.gen_golden uncond8 cond_b4: just these fixtures
+        for name in only:
+            unet_fixture(ref, name)
+        return
 
     def ref_doctree(batch, seed):
-        l4, l5 = synth_splits(batch, seed)
-        doc = ref.dual_octree.DualOctree(octree_from_splits(l4, l5, batch))
-        doc.post_processing_for_docnn()
-        return doc
+        return _ref_doctree(ref, batch, seed)
 
     # 1. dual graph of one shape: canonical sorted (row*7+dir, col) per depth
     doc = ref_doctree(1, 0)
@@ -116,18 +146,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'operators.npz'), **ops)
 
     # 4. full U-Net forwards (weights from the shared seeded_state_dict)
-    for name, cfg, batch in (('small', SMALL, 2), ('uncond', UNCOND, 1), ('cond', COND, 1)):
-        net = ref.union.UNet3DModel('hr', **cfg).eval()
-        sd = R.seeded_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 1)
-        net.load_state_dict(sd)
-        d = ref_doctree(batch, 0)
-        x = seeded_inputs(d.total_num, 3, 7)
-        ts = torch.tensor([1.5, -0.5])[:batch]
-        label = torch.tensor([1, 3])[:batch] if cfg.get('num_classes') else None
-        y = net(unet_type='hr', x=x, doctree=d, timesteps=ts, unet_lr=net.unet_lr, label=label)
-        np.savez_compressed(os.path.join(OUT, 'unet_%s.npz' % name), y=y.numpy(), x_sum=checksum(x),
-                            w_sum=sum(checksum(v) for v in sd.values()), batch=batch)
-        print(name, 'out absmax', float(y.abs().max()), 'N', d.total_num)
+    for name in UNET_CASES:
+        unet_fixture(ref, name)
     # 5. GraphVAE decoder: decode_code(update_octree=True) of the unmodified reference
     import importlib
     from tests import util as U

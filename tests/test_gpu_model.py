@@ -5,7 +5,8 @@ import pytest
 import torch
 
 from oracle import restate as R
-from tests.util import relerr, oracle_doctree, product_doctree, model_shapes, build_product, UNCOND, COND, SMALL
+from tests.util import (relerr, oracle_doctree, product_doctree, model_shapes, build_product, UNCOND, COND, SMALL,
+                        UNET_CASES, UNET_TS, UNET_LABEL)
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -120,21 +121,23 @@ def test_sampler_cuda_graph_matches_eager_and_oracle():
 # ------------------------------------------------------------------------------------------------
 # against the committed golden vectors (outputs of the unmodified reference, tests/golden/)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('name', ['small', 'uncond', 'cond'])
+@pytest.mark.parametrize('name', list(UNET_CASES))
 @pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
 def test_unet_against_reference_golden(name, dtype, tol):
+    """includes `uncond8` = the benchmarked configuration (8 latent channels: first conv K = 7*(8+5), output conv
+    128 -> 8 on the N=16 tile) at B=2 and `cond_b4` = the cond config at the 4-shapes-per-GPU shard of configs[4]."""
     import os
     import numpy as np
     from tests.util import GOLDEN
-    cfg = {'uncond': UNCOND, 'cond': COND, 'small': SMALL}[name]
+    cfg, batch, cc = UNET_CASES[name]
     g = np.load(os.path.join(GOLDEN, 'unet_%s.npz' % name))
-    batch = int(g['batch'])
+    assert batch == int(g['batch'])
     sd = R.seeded_state_dict(model_shapes(cfg), 1)
     net = build_product(cfg, sd)
     doc = product_doctree(batch, 0)
-    x = _rand((doc.total_num, 3), 7)
-    ts = torch.tensor([1.5, -0.5])[:batch]
-    label = torch.tensor([1, 3])[:batch].to(DEV) if cfg.get('num_classes') else None
+    x = _rand((doc.total_num, cc), 7)
+    ts = torch.tensor(UNET_TS)[:batch]
+    label = torch.tensor(UNET_LABEL)[:batch].to(DEV) if cfg.get('num_classes') else None
     y = net(unet_type='hr', x=x.to(DEV).to(dtype), doctree=doc, timesteps=ts.to(DEV), unet_lr=net.unet_lr, label=label)
     e = relerr(y.cpu(), torch.from_numpy(g['y']))
     assert e < tol, e

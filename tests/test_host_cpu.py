@@ -162,3 +162,19 @@ def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
         assert int(out['off_' + f]) == getattr(g, f).offset, f
     assert int(out['sizeof_octree_levels']) == C.sizeof(o)
     assert int(out['off_nnum']) == o.nnum.offset and int(out['off_full_depth']) == o.full_depth.offset
+
+
+@pytest.mark.parametrize('steps', [4, 10, 50, 100, 200, 1000])
+def test_stage1_truncation_compares_in_float32_like_the_reference(steps):
+    """reference octfusion_model_union.py:324 / :339 compare float32 time tensors against the Python scalar 0.7
+    (cast to float32 by torch); linspace(1, 0, steps+1) contains float32(0.7) exactly for these step counts, where a
+    float64 compare decides the other way."""
+    from octfusion_b200.sampler import truncation_flags
+    times = torch.linspace(1.0, 0.0, steps + 1)
+    pairs = torch.stack((times[:-1], times[1:]), 0).unbind(-1)        # get_sampling_timesteps (:292-298), one sample
+    do_sign, add_noise = truncation_flags(steps, 0.7)
+    for i, (t, tn) in enumerate(pairs):
+        assert do_sign[i] == bool(t < 0.7) and add_noise[i] == bool(tn > 0.7), i
+    if steps >= 10:
+        k = [i for i in range(steps) if float(times[i]) < 0.7 and not do_sign[i]]
+        assert len(k) == 1          # the one step a double-precision compare would get wrong

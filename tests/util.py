@@ -17,6 +17,13 @@ COND = dict(UNCOND, num_res_blocks=[[1, 1, 1], [2, 2, 0]], attention_resolutions
             channel_mult=[[1, 2, 4, 8], [1, 2, 4]], num_classes=5)
 # a narrow net with the same topology: fast enough for CPU-side tests and golden fixtures
 SMALL = dict(UNCOND, model_channels=[64, 64], channel_mult=[[1, 2], [1, 1, 2]], attention_resolutions=[2])
+# the benchmarked configuration (bench.py: 8 latent channels, BASELINE.json "8 feature channels")
+UNCOND8 = dict(UNCOND, input_channels=[8, 8], out_channels=[8, 8])
+# golden full-forward cases (oracle/gen_golden.py UNET_CASES): name -> (config, batch, latent channels)
+UNET_CASES = {'small': (SMALL, 2, 3), 'uncond': (UNCOND, 1, 3), 'cond': (COND, 1, 3),
+              'uncond8': (UNCOND8, 2, 8), 'cond_b4': (COND, 4, 3)}
+UNET_TS = [1.5, -0.5, 0.3, 2.2]
+UNET_LABEL = [1, 3, 0, 4]
 
 
 def relerr(a, b):
