@@ -16,7 +16,7 @@
  *   - return value: 0 = launched; negative = rejected before any launch (OF_E_*); the
  *     text of the last error of the calling thread is available from of_last_error()
  *   - dtype: OF_F32 (0) = float activations, OF_BF16 (1) = __nv_bfloat16 activations;
- *     accumulation is always fp32; statistics are accumulated in fp64
+ *     accumulation is always fp32; norm statistics: fp32 partial sums per (32-row chunk, 4 channels), combined in fp64
  *   - all row strides (ld*) are in ELEMENTS
  */
 #ifndef OCTFUSION_B200_H_
@@ -40,6 +40,13 @@ const char* of_last_error(void);
 int of_version(void);              /* ABI version, bumped on any signature change          */
 int of_num_sms(void);              /* multiprocessor count of the current device           */
 unsigned long long of_launch_count(void); /* kernels launched by this library so far (process-wide) */
+/* ABI guards: sizeof(of_gemm_args) / sizeof(of_octree_levels) as compiled into the library -- a binding whose struct
+ * mirror has a different size must refuse to run (a stale .so would otherwise read garbage pointers) */
+int of_abi_sizeof_gemm_args(void);
+int of_abi_sizeof_octree_levels(void);
+/* diagnostics: per-role clock64 stamps of CTA `block` of the following of_gather_gemm_tc launches are written to
+ * buf [7][cap_per_region] (uint64); buf = NULL switches tracing off (tools/trace_tc.py decodes the stamps) */
+int of_tc_trace_set(void* buf, int32_t cap_per_region, int32_t block);
 
 /* ------------------------------------------------------------------------------------------
  * Tap-gather GEMM:   out[m, :] = sum_tap  mean_{j in nbr(m, tap)} [ A[j, :] | onehot(type_j) ] . W[tap]
@@ -91,15 +98,26 @@ typedef struct of_gemm_args {
    * deeper octrees such as the VAE's depth 8 must pass nt_block).                                       */
   const void* a_multi; int64_t ld_multi;
   const uint64_t* multi_types;
-  /* row counts of a0 / a1 (tcgen05 path): > 0 enables the TMA gather4 half of the gather (rows beyond the
-   * count are the hardware's zero fill for empty slots); 0 = unknown -> cp.async only                       */
+  /* row counts of a0 / a1 (informational; may be 0)                                                          */
   int32_t rows_a0, rows_a1;
-  /* tcgen05 path with ntype > 0: the node-type K block as a precomputed bf16 [M, 64] tensor (of_graph_type_block,
-   * record-encoded table); NULL = build it inside the kernel for every tile (slow: dependent loads)        */
+  /* tcgen05 path with ntype > 0 (required there): the node-type K block as a precomputed bf16 [M, 64] tensor
+   * (of_graph_type_block, record-encoded table)                                                              */
   const void* nt_block;
   /* tcgen05 path: 1 = walk the row tiles from the last to the first.  Alternating the direction from one kernel to
    * the next lets each kernel start on the rows its producer wrote last, which are still in the 126 MB L2.  */
   int32_t reverse;
+  /* tcgen05 path, optional: group-norm partial statistics of the OUTPUT, computed in the epilogue from the fp32
+   * values before they are rounded to bf16 (the statistics pass of the following DualOctreeGroupNorm,
+   * modules.py:291-326, then never reads the tensor).  Rows are cut into 32-row chunks; a chunk is split into
+   * SEGMENTS at every change of sample id; stat_chunk_seg [ceil(M/32)+1] is the exclusive prefix sum of segments
+   * per chunk (of_stat_plan_* in the Python layer builds it once per graph depth).  stat_out [n_segments, N/4, 2]
+   * fp32 receives (sum, sum of squares) per 4-channel granule of every segment -- one plain store per value, no
+   * atomics, fixed summation order: bit-reproducible.  Sample of row m: stat_sample[m], or m / stat_rows_per_sample
+   * when stat_sample is NULL.  Requires N % 32 == 0 and out_rows == NULL.  NULL = off.                        */
+  float* stat_out;
+  const int32_t* stat_chunk_seg;
+  const int32_t* stat_sample;
+  int32_t stat_rows_per_sample;
 } of_gemm_args;
 
 /* CUDA-core FFMA path: any shape, fp32-exact accumulation order-insensitive to 1e-6. */
@@ -127,16 +145,25 @@ int of_repack_weight(const float* src, int64_t s_tap, int64_t s_c, int64_t s_n,
  *   GroupNorm32 (dense)           modules.py:26-28                    (count_eps = 0)
  * followed (fused) by SiLU (modules.py:743, 760, graph_unet_hr.py:272) and the channel concat.
  * x is the virtual concatenation (x0 | x1).  sample_id [rows] int32 (NULL => row / rows_per_sample).
- *   stats:    sums [B, G, 2] fp64 += (sum x, sum x^2)           (caller zeroes `sums`)
- *   finalize: scale/shift [B, C] fp32 from sums, gamma, beta, counts
- *   apply:    y[r, c] = act(x[r, c] * scale[b, c] + shift[b, c])   act: 0 none, 1 SiLU
+ * Statistics are deterministic (no atomics): rows are cut into 32-row chunks, chunks into per-sample SEGMENTS
+ * (see of_gemm_args.stat_out), and every segment owns one slot of a partial buffer.
+ *   stats:    part [n_segments, C/4, 2] fp32 = (sum x, sum x^2) per 4-channel granule of each segment, one thread
+ *             per (chunk, channel vector), rows added in order.  The tcgen05 GEMM writes the same buffer from its
+ *             epilogue (stat_out), in which case this pass is skipped.
+ *   finalize: for sample b the segments sample_seg_idx[sample_seg_off[b] .. sample_seg_off[b+1]) are summed in that
+ *             order in fp64 -> mean / variance per group -> scale/shift [B, C] fp32 (gamma, beta folded in).
+ *             The normalised tensor is the concat (x0 | x1): part0 / part1 are the partial buffers of the two
+ *             tensors (c1 = 0: one tensor).  C/groups must be a multiple of 4 and c0 % 4 == 0.
+ *   apply:    y[r, c] = act(x[r, c] * scale[b, c] + shift[b, c])   act: 0 none, 1 SiLU, 2 GELU (erf)
  * ------------------------------------------------------------------------------------------ */
 int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
-                const int32_t* sample_id, int32_t rows_per_sample, int64_t rows, int32_t batch,
-                int32_t groups, int32_t dtype, double* sums, int32_t reverse, void* stream);
-int of_gn_finalize(const double* sums, const int32_t* rows_of_sample, int32_t rows_per_sample,
-                   const float* gamma, const float* beta, int32_t batch, int32_t channels,
-                   int32_t groups, float eps, float count_eps, float* scale, float* shift, void* stream);
+                const int32_t* chunk_seg, const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
+                int32_t dtype, float* part, void* stream);
+int of_gn_finalize(const float* part0, int32_t c0, const float* part1, int32_t c1,
+                   const int32_t* sample_seg_off, const int32_t* sample_seg_idx,
+                   const int32_t* rows_of_sample, int32_t rows_per_sample,
+                   const float* gamma, const float* beta, int32_t batch, int32_t groups, float eps,
+                   float count_eps, float* scale, float* shift, void* stream);
 int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                 const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
                 const float* scale, const float* shift, int32_t act, int32_t dtype,

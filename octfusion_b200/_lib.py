@@ -39,6 +39,7 @@ class GemmArgs(C.Structure):
         ('rows_a0', _i32), ('rows_a1', _i32),
         ('nt_block', _vp),
         ('reverse', _i32),
+        ('stat_out', _vp), ('stat_chunk_seg', _vp), ('stat_sample', _vp), ('stat_rows_per_sample', _i32),
     ]
 
 
@@ -56,13 +57,17 @@ _PROTOS = {
     'of_version': (C.c_int, []),
     'of_num_sms': (C.c_int, []),
     'of_launch_count': (C.c_ulonglong, []),
+    'of_abi_sizeof_gemm_args': (C.c_int, []),
+    'of_abi_sizeof_octree_levels': (C.c_int, []),
+    'of_tc_trace_set': (C.c_int, [_vp, _i32, _i32]),
     'of_gather_gemm_simt': (C.c_int, [C.POINTER(GemmArgs), _vp]),
     'of_gather_gemm_tc': (C.c_int, [C.POINTER(GemmArgs), _vp]),
     'of_pack_weight_tc_bytes': (_i64, [_i32, _i32, _i32, _i32]),
     'of_pack_weight_tc': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'of_repack_weight': (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
-    'of_gn_stats': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _vp]),
-    'of_gn_finalize': (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp]),
+    'of_gn_stats': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _i64, _i32, _vp, _vp]),
+    'of_gn_finalize': (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _f32, _f32, _vp, _vp,
+                                 _vp]),
     'of_gn_apply': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     'of_attention': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     'of_linear_small': (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
@@ -97,20 +102,33 @@ class LibraryMissing(ImportError):
     pass
 
 
+ABI_VERSION = 2          # of_version() of the header this binding mirrors
+
+
 def _load():
     path = _build.LIB
-    if not os.path.exists(path):
+    # (re)build when the library is missing or older than a source / the header -- only where nvcc exists (the GPU
+    # box receives the prebuilt .so with the snapshot and has the same sources, so needs_build() is False there)
+    if _build.needs_build() and (not os.path.exists(path) or _build.have_nvcc()):
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001
-            raise LibraryMissing(
-                'octfusion_b200: CUDA library %s is missing and could not be built (%s). '
-                'There is no CPU fallback; run `python -m octfusion_b200.build`.' % (path, e)) from e
+            if not os.path.exists(path):
+                raise LibraryMissing(
+                    'octfusion_b200: CUDA library %s is missing and could not be built (%s). '
+                    'There is no CPU fallback; run `python -m octfusion_b200.build`.' % (path, e)) from e
+            raise
     lib = C.CDLL(path)
     for name, (res, args) in _PROTOS.items():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
+    # a stale library with another struct layout would read garbage pointers: refuse it
+    got = (lib.of_version(), lib.of_abi_sizeof_gemm_args(), lib.of_abi_sizeof_octree_levels())
+    want = (ABI_VERSION, C.sizeof(GemmArgs), C.sizeof(OctreeLevels))
+    if got != want:
+        raise LibraryMissing('octfusion_b200: %s has ABI (version, sizeof gemm_args, sizeof octree_levels) = %s, this '
+                             'binding expects %s -- rebuild with `python -m octfusion_b200.build --force`' % (path, got, want))
     return lib
 
 

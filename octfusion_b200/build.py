@@ -24,6 +24,12 @@ def _nvcc():
     return 'nvcc'
 
 
+def have_nvcc() -> bool:
+    import shutil
+    c = _nvcc()
+    return os.path.exists(c) if os.path.isabs(c) else shutil.which(c) is not None
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True

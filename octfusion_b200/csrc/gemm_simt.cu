@@ -141,6 +141,10 @@ int check_gemm_args(const of_gemm_args* a, const char* who) {
 extern "C" int of_gather_gemm_simt(const of_gemm_args* args, void* stream) {
   int rc = of::check_gemm_args(args, "of_gather_gemm_simt");
   if (rc) return rc;
+  if (args->stat_out != nullptr) {
+    of::set_error("of_gather_gemm_simt: stat_out is a tcgen05-path feature (run of_gn_stats on the output instead)");
+    return OF_E_UNSUPPORTED;
+  }
   if (args->M == 0) return OF_OK;
   dim3 grid((args->M + of::SBM - 1) / of::SBM, (args->N + of::SBN - 1) / of::SBN);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -3,8 +3,9 @@
 // Replaces DualOctreeGroupNorm.forward (reference models/networks/modules.py:291-326: three
 // scatter_add passes, two index_select passes and six elementwise passes = ~12 HBM round trips)
 // and the dense GroupNorm32 (modules.py:26-28) by
-//   of_gn_stats     one read  of x            -> per (sample, group) sum / sum of squares (fp64)
-//   of_gn_finalize  [B, C] scale / shift table (fp64 arithmetic, fp32 result)
+//   of_gn_stats     one read  of x            -> per (32-row segment, 4-channel granule) sum / sum of squares in fp32,
+//                   no atomics (bit-reproducible); skipped when the producing tcgen05 GEMM wrote the partials itself
+//   of_gn_finalize  partials summed in fixed order in fp64 -> [B, C] scale / shift table (fp32 result)
 //   of_gn_apply     one read + one write      -> y = SiLU(x * scale + shift), concat fused
 // HBM-bound kernels: 16-byte vector accesses, grid sized in multiples of the SM count.
 #include "common.cuh"
@@ -28,6 +29,13 @@ template <>
 __device__ __forceinline__ void load_vec<__nv_bfloat16, 8>(const __nv_bfloat16* p, float* f) {
   uint4 q = *reinterpret_cast<const uint4*>(p);
   bf16x8_to_f32(q, f);
+}
+template <>
+__device__ __forceinline__ void load_vec<__nv_bfloat16, 4>(const __nv_bfloat16* p, float* f) {
+  const uint2 q = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
 template <>
 __device__ __forceinline__ void load_vec<__nv_bfloat16, 1>(const __nv_bfloat16* p, float* f) {
@@ -78,105 +86,118 @@ __device__ __forceinline__ bool chunk_is_uniform(const GnSrc& s, int64_t r0, int
   return (int)((r1 - 1) / s.rows_per_sample) == b0;
 }
 
-// bins: dynamic smem float [batch][groups][2]
+// Deterministic partial statistics: one thread per (32-row chunk, channel vector) adds its rows in order and writes
+// (sum, sum of squares) per 4-channel granule into the slot of the chunk's segment -- the layout the tcgen05 GEMM
+// epilogue produces (of_gemm_args.stat_out), so of_gn_finalize serves both.  A new segment starts at every change
+// of sample id inside the chunk.
 template <typename T, int V>
-__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int batch, int groups, int chunk, int reverse, double* sums) {
-  extern __shared__ float bins[];
+__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* __restrict__ chunk_seg, float* __restrict__ part) {
   const int C = s.c0 + s.c1;
-  const int cpg = C / groups;
-  const int tpr = C / V;                                   // threads per row
-  const int rp = blockDim.x / tpr;                         // rows in flight (>= 1 checked on host)
-  const int64_t r0 = (int64_t)((reverse & 1) ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * chunk;
-  const int64_t r1 = min(r0 + (int64_t)chunk, s.rows);
-  const bool active = (int)threadIdx.x < rp * tpr;
-  const int cv = (threadIdx.x % tpr) * V;
-  // per-thread source: the channel vector lives in x0 or in x1 (fused concat)
+  const int tpr = C / V;                                   // threads per chunk
+  const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t chunk = gidx / tpr;
+  const int cv = (int)(gidx - chunk * tpr) * V;
+  const int64_t r0 = chunk * 32;
+  if (r0 >= s.rows) return;
+  const int64_t r1 = min(r0 + 32, s.rows);
   const T* base = cv < s.c0 ? reinterpret_cast<const T*>(s.x0) + cv : reinterpret_cast<const T*>(s.x1) + (cv - s.c0);
   const int64_t ld = cv < s.c0 ? s.ld0 : s.ld1;
-  int b0;
-  const bool uniform = chunk_is_uniform(s, r0, r1, b0) && !(reverse & 2);
-  const int nbins = (uniform ? 1 : batch) * groups * 2;
-  for (int i = threadIdx.x; i < nbins; i += blockDim.x) bins[i] = 0.0f;
-  __syncthreads();
-  if (active) {
-    float sum[V], sq[V];
+  constexpr int G = V / 4 > 0 ? V / 4 : 1;                 // granules per thread (V = 4 or 8)
+  float sum[G], sq[G];
 #pragma unroll
-    for (int i = 0; i < V; ++i) { sum[i] = 0.0f; sq[i] = 0.0f; }
-    int cur_b = -1;
-    auto flush = [&](int slot) {
-      // combine channels that fall in the same group before touching shared memory
-      int g_prev = (cv) / cpg;
-      float a = 0.0f, b = 0.0f;
+  for (int i = 0; i < G; ++i) { sum[i] = 0.0f; sq[i] = 0.0f; }
+  int seg = chunk_seg[chunk];
+  const int half = C >> 1;                                 // floats per segment slot
+  auto sample_of = [&](int64_t r) { return s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample); };
+  int cur = sample_of(r0);
+  auto flush = [&]() {
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const int g = (cv + i) / cpg;
-        if (g != g_prev) {
-          atomicAdd(&bins[(slot * groups + g_prev) * 2], a);
-          atomicAdd(&bins[(slot * groups + g_prev) * 2 + 1], b);
-          a = 0.0f; b = 0.0f; g_prev = g;
-        }
-        a += sum[i]; b += sq[i];
-        sum[i] = 0.0f; sq[i] = 0.0f;
-      }
-      atomicAdd(&bins[(slot * groups + g_prev) * 2], a);
-      atomicAdd(&bins[(slot * groups + g_prev) * 2 + 1], b);
-    };
-    int64_t r = r0 + threadIdx.x / tpr;
-    if (uniform) {
-      for (; r + (GN_UNROLL - 1) * rp < r1; r += GN_UNROLL * rp) {
-        float f[GN_UNROLL][V];
+    for (int i = 0; i < G; ++i) {
+      *reinterpret_cast<float2*>(part + (int64_t)seg * half + ((cv >> 2) + i) * 2) = make_float2(sum[i], sq[i]);
+      sum[i] = 0.0f; sq[i] = 0.0f;
+    }
+  };
+  for (int64_t r = r0; r < r1; r += 8) {
+    float f[8][V];
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) load_vec<T, V>(base + (r + u * rp) * ld, f[u]);
+    for (int u = 0; u < 8; ++u)
+      if (r + u < r1) load_vec<T, V>(base + (r + u) * ld, f[u]);
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u)
+    for (int u = 0; u < 8; ++u) {
+      if (r + u >= r1) break;
+      const int b = sample_of(r + u);
+      if (b != cur) { flush(); ++seg; cur = b; }
 #pragma unroll
-          for (int i = 0; i < V; ++i) { sum[i] += f[u][i]; sq[i] = fmaf(f[u][i], f[u][i], sq[i]); }
-      }
-      for (; r < r1; r += rp) {
-        float f[V];
-        load_vec<T, V>(base + r * ld, f);
-#pragma unroll
-        for (int i = 0; i < V; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
-      }
-      flush(0);
-    } else {
-      for (; r < r1; r += rp) {
-        const int b = s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample);
-        if (b != cur_b) { if (cur_b >= 0) flush(cur_b); cur_b = b; }
-        float f[V];
-        load_vec<T, V>(base + r * ld, f);
-#pragma unroll
-        for (int i = 0; i < V; ++i) { sum[i] += f[i]; sq[i] = fmaf(f[i], f[i], sq[i]); }
-      }
-      if (cur_b >= 0) flush(cur_b);
+      for (int i = 0; i < V; ++i) { sum[i / 4] += f[u][i]; sq[i / 4] = fmaf(f[u][i], f[u][i], sq[i / 4]); }
     }
   }
-  __syncthreads();
-  double* dst = sums + (uniform ? (int64_t)b0 * groups * 2 : 0);
-  for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
-    const float v = bins[i];
-    if (v != 0.0f) atomicAdd(&dst[i], (double)v);
-  }
+  flush();
 }
 
-__global__ void gn_finalize_kernel(const double* __restrict__ sums, const int32_t* __restrict__ rows_of_sample,
-                                   int rows_per_sample, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, int batch, int C, int groups, float eps,
-                                   float count_eps, float* __restrict__ scale, float* __restrict__ shift) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= batch * C) return;
-  const int b = i / C, c = i - b * C;
-  const int cpg = C / groups, g = c / cpg;
+// One CTA per sample: partial slots of the sample's segments are summed in list order (fixed order, fp64), then the
+// group statistics and the [C] scale / shift rows of the sample are formed.
+//   smem: double red[slices][nval] | double tot[nval]
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ part0, int c0, const float* __restrict__ part1,
+                                                            int c1, const int32_t* __restrict__ seg_off,
+                                                            const int32_t* __restrict__ seg_idx,
+                                                            const int32_t* __restrict__ rows_of_sample, int rows_per_sample,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            int groups, float eps, float count_eps, float* __restrict__ scale,
+                                                            float* __restrict__ shift) {
+  extern __shared__ double gn_sm[];
+  const int b = blockIdx.x;
+  const int C = c0 + c1;
+  const int nval = C >> 1;                                 // (sum, sumsq) x C/4 granules
+  const int h0 = c0 >> 1, h1 = c1 >> 1;
+  const int slices = blockDim.x / nval;                    // >= 1 (checked on host)
+  double* red = gn_sm;
+  double* tot = gn_sm + (size_t)slices * nval;
+  const int j = threadIdx.x % nval, sl = threadIdx.x / nval;
+  const int k0 = seg_off[b], k1 = seg_off[b + 1];
+  if (sl < slices) {
+    // contiguous sub-range of the sample's segment list for this slice; four interleaved accumulators, fixed order
+    const int n = k1 - k0;
+    const int per = (n + slices - 1) / slices;
+    const int a = k0 + sl * per, e = min(a + per, k1);
+    const float* src = j < h0 ? part0 + j : part1 + (j - h0);
+    const int64_t stride = j < h0 ? h0 : h1;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int k = a;
+    for (; k + 3 < e; k += 4) {
+      int s4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] = seg_idx[k + u];
+      float v4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v4[u] = src[(int64_t)s4[u] * stride];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += (double)v4[u];
+    }
+    for (int u = 0; k < e; ++k, ++u) acc[u] += (double)src[(int64_t)seg_idx[k] * stride];
+    red[(size_t)sl * nval + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nval) {
+    double t = 0.0;
+    for (int q = 0; q < slices; ++q) t += red[(size_t)q * nval + threadIdx.x];
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const int cpg = C / groups;
   const double n = (double)(rows_of_sample ? rows_of_sample[b] : rows_per_sample) * (double)cpg;
   const double inv = 1.0 / (n + (double)count_eps);      // modules.py:302: eps joins the COUNT
-  const double S = sums[(b * groups + g) * 2], Q = sums[(b * groups + g) * 2 + 1];
-  const double m = S * inv;                                // modules.py:304
-  double var = (Q - 2.0 * m * S + n * m * m) * inv;        // sum (x-m)^2 * inv_count, modules.py:308
-  if (var < 0.0) var = 0.0;
-  const double rstd = 1.0 / sqrt(var + (double)eps);       // modules.py:310
-  const double ga = gamma[c];
-  scale[i] = (float)(rstd * ga);
-  shift[i] = (float)((double)beta[c] - m * rstd * ga);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    double S = 0.0, Q = 0.0;
+    for (int q = g * cpg / 4; q < (g + 1) * cpg / 4; ++q) { S += tot[2 * q]; Q += tot[2 * q + 1]; }
+    const double m = S * inv;                              // modules.py:304
+    double var = (Q - 2.0 * m * S + n * m * m) * inv;      // sum (x-m)^2 * inv_count, modules.py:308
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);     // modules.py:310
+    const double ga = gamma[c];
+    scale[(int64_t)b * C + c] = (float)(rstd * ga);
+    shift[(int64_t)b * C + c] = (float)((double)beta[c] - m * rstd * ga);
+  }
 }
 
 template <typename T> struct FastAct;
@@ -281,55 +302,54 @@ static int check_src(const GnSrc& s, const char* who) {
 }  // namespace of
 
 extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
-                           const int32_t* sample_id, int32_t rows_per_sample, int64_t rows, int32_t batch,
-                           int32_t groups, int32_t dtype, double* sums, int32_t reverse, void* stream) {
+                           const int32_t* chunk_seg, const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
+                           int32_t dtype, float* part, void* stream) {
   using namespace of;
   GnSrc s{x0, ld0, c0, x1, ld1, c1, sample_id, rows_per_sample, rows};
   int rc = check_src(s, "of_gn_stats");
   if (rc) return rc;
   const int C = c0 + c1;
-  OF_REQUIRE(groups > 0 && C % groups == 0, "of_gn_stats: C=%d not divisible by groups=%d", C, groups);
-  OF_REQUIRE(batch > 0 && sums != nullptr, "of_gn_stats: bad batch/sums");
+  OF_REQUIRE(chunk_seg != nullptr && part != nullptr, "of_gn_stats: null chunk_seg/part");
   OF_REQUIRE(dtype == OF_F32 || dtype == OF_BF16, "of_gn_stats: bad dtype");
+  const int esz = dtype == OF_F32 ? 4 : 2;
+  int V = dtype == OF_F32 ? 4 : 8;
+  if (V == 8 && !(C % 8 == 0 && vec_ok(x0, ld0, c0, 8, 2) && vec_ok(x1, ld1, c1, 8, 2))) V = 4;
+  OF_REQUIRE(C % V == 0 && c0 % V == 0, "of_gn_stats: channel counts must be multiples of %d (C=%d c0=%d)", V, C, c0);
+  OF_REQUIRE(vec_ok(x0, ld0, c0, V, esz) && vec_ok(x1, ld1, c1, V, esz),
+             "of_gn_stats: x0/x1 must be %d-byte aligned with ld %% %d == 0", V * esz, V);
   if (rows == 0) return OF_OK;
-  const size_t smem = (size_t)batch * groups * 2 * sizeof(float);
-  OF_REQUIRE(smem <= 200 * 1024, "of_gn_stats: batch*groups too large for the shared bins (%zu B)", smem);
-  const int chunk = gn_chunk_rows(C, dtype == OF_F32 ? 4 : 2);
-  const int grid = (int)((rows + chunk - 1) / chunk);
+  const int64_t chunks = (rows + 31) / 32;
+  const int64_t threads = chunks * (C / V);
+  const int grid = (int)((threads + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define OF_GN_STATS_LAUNCH(T, V)                                                                      \
-  do {                                                                                                \
-    OF_REQUIRE(C / V <= 256, "of_gn_stats: C=%d too wide", C);                                        \
-    static size_t cfg = 48 * 1024;                                                                    \
-    if (smem > cfg) {                                                                                 \
-      cudaFuncSetAttribute(gn_stats_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-      cfg = 200 * 1024;                                                                               \
-    }                                                                                                 \
-    gn_stats_kernel<T, V><<<grid, 256, smem, st>>>(s, batch, groups, chunk, reverse, sums);                           \
-  } while (0)
-  if (dtype == OF_F32) {
-    if (vec_ok(x0, ld0, c0, 4, 4) && vec_ok(x1, ld1, c1, 4, 4)) OF_GN_STATS_LAUNCH(float, 4);
-    else OF_GN_STATS_LAUNCH(float, 1);
-  } else {
-    if (vec_ok(x0, ld0, c0, 8, 2) && vec_ok(x1, ld1, c1, 8, 2)) OF_GN_STATS_LAUNCH(__nv_bfloat16, 8);
-    else OF_GN_STATS_LAUNCH(__nv_bfloat16, 1);
-  }
-#undef OF_GN_STATS_LAUNCH
+  if (dtype == OF_F32) gn_stats_kernel<float, 4><<<grid, 256, 0, st>>>(s, chunk_seg, part);
+  else if (V == 8) gn_stats_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(s, chunk_seg, part);
+  else gn_stats_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(s, chunk_seg, part);
   OF_LAUNCH_CHECK("of_gn_stats");
   return OF_OK;
 }
 
-extern "C" int of_gn_finalize(const double* sums, const int32_t* rows_of_sample, int32_t rows_per_sample,
-                              const float* gamma, const float* beta, int32_t batch, int32_t channels,
-                              int32_t groups, float eps, float count_eps, float* scale, float* shift,
-                              void* stream) {
+extern "C" int of_gn_finalize(const float* part0, int32_t c0, const float* part1, int32_t c1,
+                              const int32_t* sample_seg_off, const int32_t* sample_seg_idx,
+                              const int32_t* rows_of_sample, int32_t rows_per_sample, const float* gamma,
+                              const float* beta, int32_t batch, int32_t groups, float eps, float count_eps,
+                              float* scale, float* shift, void* stream) {
   using namespace of;
-  OF_REQUIRE(sums && gamma && beta && scale && shift, "of_gn_finalize: null pointer");
-  OF_REQUIRE(groups > 0 && channels % groups == 0, "of_gn_finalize: bad groups");
+  OF_REQUIRE(part0 && gamma && beta && scale && shift && sample_seg_off && sample_seg_idx, "of_gn_finalize: null pointer");
+  OF_REQUIRE((part1 == nullptr) == (c1 == 0), "of_gn_finalize: part1/c1 inconsistent");
+  const int C = c0 + c1;
+  OF_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 4 == 0 && c0 % 4 == 0 && c1 % 4 == 0,
+             "of_gn_finalize: C=%d groups=%d c0=%d: channels per group and c0 must be multiples of 4", C, groups, c0);
   OF_REQUIRE(rows_of_sample != nullptr || rows_per_sample > 0, "of_gn_finalize: need a row count");
-  const int n = batch * channels;
-  gn_finalize_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      sums, rows_of_sample, rows_per_sample, gamma, beta, batch, channels, groups, eps, count_eps, scale, shift);
+  OF_REQUIRE(batch > 0, "of_gn_finalize: bad batch");
+  const int nval = C / 2;
+  OF_REQUIRE(nval <= 1024, "of_gn_finalize: C=%d too wide", C);
+  const int slices = 1024 / nval;
+  const int threads = slices * nval;
+  const size_t smem = ((size_t)slices * nval + nval) * sizeof(double);
+  gn_finalize_kernel<<<batch, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      part0, c0, part1, c1, sample_seg_off, sample_seg_idx, rows_of_sample, rows_per_sample, gamma, beta, groups, eps,
+      count_eps, scale, shift);
   OF_LAUNCH_CHECK("of_gn_finalize");
   return OF_OK;
 }

@@ -19,7 +19,7 @@ N_DIR = 7
 
 class GraphPlan:
     """Device-resident description of the depth-d dual graph."""
-    __slots__ = ('depth', 'rows', 'tap', 'node_type', 'batch_id', 'rows_of_sample', 'leaf_base',
+    __slots__ = ('depth', 'rows', 'tap', 'node_type', 'batch_id', 'rows_of_sample', 'leaf_base', 'stat',
                  'down_copy_dst', 'down_copy_rows', 'down_out_rows', 'up_copy_src', 'up_copy_rows', 'up_in_rows')
 
     def __init__(self):
@@ -119,6 +119,7 @@ class DualOctree:
             p.depth, p.rows = D, rows
             p.tap = ops.TapTable(tab, extra, N_DIR).index_multi(ntype)
             p.node_type, p.batch_id, p.rows_of_sample = ntype, bid, hist
+            p.stat = ops.StatPlan(rows, self.batch_size, sample_id=bid, rows_of_sample=hist)
             p.leaf_base = int(self.lnum[fd:D].sum())          # rows of leaves coarser than D
             self.plan[D] = p
             self.graph[D] = _LazyGraph(self, D)

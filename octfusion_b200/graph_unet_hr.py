@@ -99,7 +99,7 @@ class UNet3DModel(nn.Module):
         hs = []
         h = x.contiguous()
         if not as_middle:
-            h = self.input_blocks[0].run(h, doctree.plan[d])
+            h = self.input_blocks[0].run(h, doctree.plan[d], stats=doctree.plan[d].stat)
         hs.append(h)
         for module in self.input_blocks[1:]:
             if isinstance(module, GraphResBlockEmbed):
@@ -108,7 +108,7 @@ class UNet3DModel(nn.Module):
                 h = module(h, doctree, d)
                 d -= 1
             else:
-                h = module.run(h, doctree.plan[d])
+                h = module.run(h, doctree.plan[d], stats=doctree.plan[d].stat)
             hs.append(h)
         if unet_lr is not None:
             h = self.middle_block1.run(h, emb, doctree.plan[d], bsz, e=es[id(self.middle_block1)])

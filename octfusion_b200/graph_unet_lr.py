@@ -94,23 +94,23 @@ class UNet3DModel(nn.Module):
         for resnet, attn, down in self.downs:
             x = resnet.run(x, emb, t, r, e=es[id(resnet)])
             if isinstance(attn, NormActAttention):
-                x = attn.run(x, batch, 8 ** r)
+                x = attn.run(x, t, r)
             skips.append(x)
             if isinstance(down, ConvDownsample):
                 x = down.run(x, t, r)
                 r -= 1
         x = self.mid_block1.run(x, emb, t, r, e=es[id(self.mid_block1)])
         if isinstance(self.mid_self_attn, NormActAttention):
-            x = self.mid_self_attn.run(x, batch, 8 ** r)
+            x = self.mid_self_attn.run(x, t, r)
         x = self.mid_block2.run(x, emb, t, r, e=es[id(self.mid_block2)])
         for resnet, attn, up in self.ups:
             x = resnet.run(x, emb, t, r, x1=skips.pop(), e=es[id(resnet)])
             if isinstance(attn, NormActAttention):
-                x = attn.run(x, batch, 8 ** r)
+                x = attn.run(x, t, r)
             if isinstance(up, ConvUpsample):
                 x = up.run(x, t, r)
                 r += 1
-        x = self.end[0].run(x, batch, 8 ** r, act=True)
+        x = self.end[0].run(x, t, r, act=True)
         if as_middle:
             return x
         return self.out.run(x, t.conv(r))
@@ -133,7 +133,7 @@ class UNet3DModel(nn.Module):
             sc = torch.zeros_like(x) if x_self_cond is None else x_self_cond
             xm, r = _to_morton(x, t)
             sm, _ = _to_morton(sc, t)
-            xm = self.input_emb.run(xm, t.conv(r), x1=sm)
+            xm = self.input_emb.run(xm, t.conv(r), x1=sm, stats=t.stat_plan(r))
         else:
             xm, r = _to_morton(x, t)
         y = self.run(xm, timesteps, label, b, r, as_middle)

@@ -109,8 +109,8 @@ class DualOctreeGroupNorm(nn.Module):
         self.bias = nn.Parameter(torch.zeros(1, in_channels))
 
     def run(self, x0, plan, batch_size, x1=None, act=False):
-        return ops.group_norm(x0, self.weights, self.bias, self.group, batch_size, x1=x1, sample_id=plan.batch_id,
-                              rows_of_sample=plan.rows_of_sample, eps=self.eps, count_eps=self.eps, act=act)
+        return ops.group_norm(x0, self.weights, self.bias, self.group, plan.stat, x1=x1, eps=self.eps,
+                              count_eps=self.eps, act=act)
 
     @torch.no_grad()
     def forward(self, data, doctree, depth):
@@ -200,7 +200,7 @@ class GraphDownsample(nn.Module):
         # epilogue scatters the result to the parent's row
         xd = x[pd.leaf_base:].view(-1, 8 * c)
         ops.gather_gemm(xd, self.downsample.prepared(), out=mid, out_rows=pd.down_out_rows)
-        return self.conv.run(mid, pc)
+        return self.conv.run(mid, pc, stats=pc.stat)
 
 
 class GraphUpsample(nn.Module):
@@ -223,7 +223,7 @@ class GraphUpsample(nn.Module):
         # result *is* the [8M, C] block of children rows, written in place
         tail = mid[pc.up_copy_rows:]
         ops.gather_gemm(x, self.upsample.prepared(), in_rows=pc.up_in_rows, out=tail, ldo=8 * c)
-        return self.conv.run(mid, pf)
+        return self.conv.run(mid, pf, stats=pf.stat)
 
 
 class TimestepBlock(nn.Module):
@@ -296,7 +296,7 @@ class GraphResBlockEmbed(TimestepBlock):
         lin = self.emb_layers[1]
         if e is None:
             e = ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
-        h = self.conv1.run(h, plan, row_add=e, row_add_idx=plan.batch_id)
+        h = self.conv1.run(h, plan, row_add=e, row_add_idx=plan.batch_id, stats=plan.stat)
         h = self.block2_norm.run(h, plan, batch_size, act=True)
         if isinstance(self.skip_connection, Conv1x1):
             skip = self.skip_connection.run(x0, x1)
@@ -304,7 +304,7 @@ class GraphResBlockEmbed(TimestepBlock):
             skip = x0
         else:
             skip = _concat_rows(x0, x1)          # identity skip of a concatenated input (e.g. 256+256 -> 512)
-        return self.conv2.run(h, plan, resid=skip)
+        return self.conv2.run(h, plan, resid=skip, stats=plan.stat)      # (the next block's norm consumes it)
 
     @torch.no_grad()
     def forward(self, x, emb, doctree, depth):
@@ -320,7 +320,7 @@ class DenseTables:
 
     def __init__(self, batch: int, device):
         self.batch, self.device = batch, device
-        self._tabs, self._sid, self._perm = {}, {}, {}
+        self._tabs, self._sid, self._perm, self._stat = {}, {}, {}, {}
 
     def conv(self, res_log2):
         return self._get(0, res_log2)
@@ -336,6 +336,13 @@ class DenseTables:
         if k not in self._tabs:
             self._tabs[k] = ops.dense_tap_table(mode, r, self.batch, self.device)
         return self._tabs[k]
+
+    def stat_plan(self, res_log2):
+        """segment tables of the norm statistics for the [B * 8^r, C] layout (ops.StatPlan)"""
+        if res_log2 not in self._stat:
+            v = 8 ** res_log2
+            self._stat[res_log2] = ops.StatPlan(self.batch * v, self.batch, rows_per_sample=v, device=self.device)
+        return self._stat[res_log2]
 
     def sample_id(self, res_log2):
         if res_log2 not in self._sid:
@@ -374,9 +381,9 @@ def _from_morton(y, tables, b, r):
 class GroupNorm32(nn.GroupNorm):
     """reference modules.py:26-28 (statistics in fp32; here fp64 accumulators)."""
 
-    def run(self, x0, batch, rows_per_sample, x1=None, act=False):
-        return ops.group_norm(x0, self.weight, self.bias, self.num_groups, batch, x1=x1,
-                              rows_per_sample=rows_per_sample, eps=self.eps, count_eps=0.0, act=act)
+    def run(self, x0, tables, res_log2, x1=None, act=False):
+        return ops.group_norm(x0, self.weight, self.bias, self.num_groups, tables.stat_plan(res_log2), x1=x1,
+                              eps=self.eps, count_eps=0.0, act=act)
 
 
 def convnormalization(channels):
@@ -437,7 +444,7 @@ class ConvDownsample(nn.Module):
         self.op = conv_nd(dims, channels, channels, 3, stride=2, padding=1)
 
     def run(self, x, tables, res_log2):
-        return self.op.run(x, tables.down(res_log2 - 1))
+        return self.op.run(x, tables.down(res_log2 - 1), stats=tables.stat_plan(res_log2 - 1))
 
     @torch.no_grad()
     def forward(self, x):
@@ -456,7 +463,7 @@ class ConvUpsample(nn.Module):
         self.conv = conv_nd(dims, channels, channels, 3, padding=1)
 
     def run(self, x, tables, res_log2):
-        return self.conv.run(x, tables.up(res_log2 + 1))
+        return self.conv.run(x, tables.up(res_log2 + 1), stats=tables.stat_plan(res_log2 + 1))
 
     @torch.no_grad()
     def forward(self, x):
@@ -484,18 +491,17 @@ class ResnetBlock(nn.Module):
         self._pw_t = PreparedWeight(1, emb_dim, 0, dim_out)
 
     def run(self, x0, emb, tables, res_log2, x1=None, e=None):
-        b, v = tables.batch, 8 ** res_log2
-        tap = tables.conv(res_log2)
-        h = self.block1[0].run(x0, b, v, x1=x1, act=True)
+        tap, sp = tables.conv(res_log2), tables.stat_plan(res_log2)
+        h = self.block1[0].run(x0, tables, res_log2, x1=x1, act=True)
         lin = self.time_mlp[1]
         t = e if e is not None else ops.linear_small(emb, lin.weight, lin.bias, a_silu=True)
-        h = self.block1[2].run(h, tap, row_add=t, row_add_idx=tables.sample_id(res_log2))
-        h = self.block2[0].run(h, b, v, act=True)
+        h = self.block1[2].run(h, tap, row_add=t, row_add_idx=tables.sample_id(res_log2), stats=sp)
+        h = self.block2[0].run(h, tables, res_log2, act=True)
         if isinstance(self.res_conv, nn.Identity):
             skip = x0 if x1 is None else _concat_rows(x0, x1)
         else:
             skip = ops.gather_gemm(x0, self.res_conv.prepared(), a1=x1, bias=self.res_conv.bias)
-        return self.block2[3].run(h, tap, resid=skip)
+        return self.block2[3].run(h, tap, resid=skip, stats=sp)
 
     @torch.no_grad()
     def forward(self, x, time_emb, text_condition=None):
@@ -526,19 +532,21 @@ class AttentionBlock(nn.Module):
         self.attention = QKVAttention()
         self.proj_out = zero_module(conv_nd(1, channels, channels, 1))
 
-    def run(self, x, batch, tokens):
-        """x [B*T, C] channels-last."""
-        h = self.norm.run(x, batch, tokens)
+    def run(self, x, tables, res_log2):
+        """x [B*T, C] channels-last Morton rows, T = 8^res_log2."""
+        h = self.norm.run(x, tables, res_log2)
         qkv = self.qkv.run(h)
-        a = ops.attention(qkv, batch, tokens, self.num_heads)
-        return self.proj_out.run(a, resid=x)
+        a = ops.attention(qkv, tables.batch, 8 ** res_log2, self.num_heads)
+        return self.proj_out.run(a, resid=x, stats=tables.stat_plan(res_log2))
 
     @torch.no_grad()
     def forward(self, x):
         b, c = x.shape[:2]
         xf = x.reshape(b, c, -1)
         t = xf.shape[2]
-        y = self.run(xf.permute(0, 2, 1).reshape(b * t, c).contiguous(), b, t)
+        r = int(round(math.log2(t) / 3))
+        assert 8 ** r == t, 'AttentionBlock: token count must be a power of 8 (a cubic grid)'
+        y = self.run(xf.permute(0, 2, 1).reshape(b * t, c).contiguous(), DenseTables(b, x.device), r)
         return y.reshape(b, t, c).permute(0, 2, 1).reshape(x.shape).contiguous()
 
 
@@ -549,8 +557,8 @@ class NormActAttention(nn.Sequential):
     def __init__(self, channels, num_heads):
         super().__init__(convnormalization(channels), activation_function(), AttentionBlock(channels, num_heads))
 
-    def run(self, x, batch, tokens):
-        return self[2].run(self[0].run(x, batch, tokens, act=True), batch, tokens)
+    def run(self, x, tables, res_log2):
+        return self[2].run(self[0].run(x, tables, res_log2, act=True), tables, res_log2)
 
 
 class LearnedSinusoidalPosEmb(nn.Module):

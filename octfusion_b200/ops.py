@@ -84,6 +84,56 @@ class TapTable:
         return self
 
 
+class StatPlan:
+    """Segment tables of the deterministic group-norm statistics for one row layout (include/octfusion_b200.h,
+    of_gemm_args.stat_out): rows are cut into 32-row chunks, a chunk into segments at every change of sample id.
+      chunk_seg      int32 [n_chunks + 1]  exclusive prefix sum of segments per chunk
+      sample_seg_off int32 [B + 1], sample_seg_idx int32 [n_seg]: the segments of each sample, in row order
+    Built once per graph depth (sample ids from DualOctree.batch_id) or per dense resolution (rows_per_sample)."""
+    __slots__ = ('rows', 'batch', 'n_seg', 'chunk_seg', 'sample_seg_off', 'sample_seg_idx', 'sample_id',
+                 'rows_per_sample', 'rows_of_sample')
+
+    def __init__(self, rows: int, batch: int, *, sample_id=None, rows_per_sample=0, rows_of_sample=None, device=None):
+        assert (sample_id is None) != (rows_per_sample == 0)
+        dev = sample_id.device if sample_id is not None else torch.device(device)
+        self.rows, self.batch = rows, batch
+        self.sample_id, self.rows_per_sample, self.rows_of_sample = sample_id, rows_per_sample, rows_of_sample
+        r = torch.arange(rows, device=dev)
+        bid = sample_id.long() if sample_id is not None else r // rows_per_sample
+        new = torch.ones(rows, dtype=torch.bool, device=dev)
+        if rows > 1:
+            new[1:] = (bid[1:] != bid[:-1]) | ((r[1:] & 31) == 0)
+        seg_of_row = torch.cumsum(new.int(), 0) - 1
+        n_chunks = (rows + 31) // 32
+        self.n_seg = int(seg_of_row[-1].item()) + 1 if rows > 0 else 0      # (one sync, once per layout)
+        cs = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
+        cs[:n_chunks] = seg_of_row[::32].int()
+        cs[n_chunks] = self.n_seg
+        self.chunk_seg = cs
+        seg_sample = bid[new]
+        order = torch.sort(seg_sample, stable=True).indices
+        self.sample_seg_idx = order.int().contiguous()
+        cnt = torch.bincount(seg_sample, minlength=batch)
+        off = torch.zeros(batch + 1, dtype=torch.int32, device=dev)
+        off[1:] = torch.cumsum(cnt, 0).int()
+        self.sample_seg_off = off
+
+    def new_part(self, channels: int):
+        """partial buffer [n_seg, channels/4, 2] fp32 (every slot is overwritten by its producer: no zeroing)"""
+        return torch.empty((max(self.n_seg, 1), channels // 2), dtype=torch.float32, device=self.chunk_seg.device)
+
+
+class Stats:
+    """partial statistics of one tensor: (buffer, StatPlan); attached to GEMM outputs as `t._of_stats`."""
+    __slots__ = ('part', 'plan', 'channels')
+
+    def __init__(self, part, plan, channels):
+        self.part, self.plan, self.channels = part, plan, channels
+
+
+_FUSE_STATS = os.environ.get('OCTFUSION_GN_FUSE', '1') != '0'     # 0: always run the stand-alone statistics pass
+
+
 class PreparedWeight:
     """A GEMM weight in the two layouts the kernels read:
     canonical fp32 [taps*(c+ntype), N] (CUDA-core path) and the bf16 swizzled tile image (tcgen05
@@ -141,8 +191,11 @@ class PreparedWeight:
 
 def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows=None, node_type=None,
                 a_silu=False, bias=None, row_add=None, row_add_idx=None, resid=None, out_rows=None,
-                out=None, ldo=None, out_f32=False, m=None, force_simt=False):
-    """out[m,:] = sum_tap mean_nbr [a0|a1|onehot] . W[tap] + bias + row_add[row_add_idx[m]] + resid[m]."""
+                out=None, ldo=None, out_f32=False, m=None, force_simt=False, stats: StatPlan = None):
+    """out[m,:] = sum_tap mean_nbr [a0|a1|onehot] . W[tap] + bias + row_add[row_add_idx[m]] + resid[m].
+    stats: the StatPlan of the output rows when a group norm consumes the output next -- the tcgen05 epilogue then
+    writes the norm's partial statistics (attached to the result as `_of_stats`), and ops.group_norm skips its
+    statistics pass."""
     _lib.require_cuda(a0, a1, bias, row_add, resid, out)
     assert a0.dim() == 2 and a0.stride(1) == 1
     c0 = a0.shape[1]
@@ -205,6 +258,14 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g.out_f32 = 1 if (out_f32 or (out.dtype == torch.float32 and act_dtype != torch.float32)) else 0
     g.M, g.N = m, n
     g.dtype = dt(a0)
+    st_obj = None
+    g.stat_out, g.stat_chunk_seg, g.stat_sample, g.stat_rows_per_sample = None, None, None, 0
+    if (stats is not None and _FUSE_STATS and use_tc and n % 32 == 0 and out_rows is None and stats.rows == m
+            and not g.out_f32):
+        st_obj = Stats(stats.new_part(n), stats, n)
+        g.stat_out, g.stat_chunk_seg = st_obj.part.data_ptr(), stats.chunk_seg.data_ptr()
+        g.stat_sample = stats.sample_id.data_ptr() if stats.sample_id is not None else None
+        g.stat_rows_per_sample = stats.rows_per_sample
     prof = _PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -224,6 +285,8 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
                                      + (m * n * es if resid is not None else 0)),
                          start=e0, end=e1))
     _trace('gemm_tc' if use_tc else 'gemm_simt', out)
+    if st_obj is not None:
+        out._of_stats = st_obj
     return out
 
 
@@ -259,30 +322,45 @@ _gn_general = 2 if os.environ.get('OCTFUSION_GN_GENERAL') == '1' else 0      # d
 _ACT = {False: 0, None: 0, True: 1, 'silu': 1, 'gelu': 2}
 
 
-def group_norm(x0, gamma, beta, groups: int, batch: int, *, x1=None, sample_id=None, rows_per_sample=0,
-               rows_of_sample=None, eps=1e-5, count_eps=0.0, act=False, out=None):
-    """(x0|x1) -> act(groupnorm) with per-sample statistics; stats in fp64, one read + one read/write."""
+def _stats_of(x, plan: StatPlan):
+    """partials of x under `plan`: those its producing GEMM attached, else one stand-alone statistics pass"""
+    st = getattr(x, '_of_stats', None)
+    if st is not None and st.plan is plan and st.channels == x.shape[1]:
+        return st.part
+    part = plan.new_part(x.shape[1])
+    check(lib.of_gn_stats(ptr(x), x.stride(0), x.shape[1], None, 0, 0, ptr(plan.chunk_seg), ptr(plan.sample_id),
+                          plan.rows_per_sample, x.shape[0], dt(x), ptr(part), stream()), 'of_gn_stats')
+    return part
+
+
+def group_norm(x0, gamma, beta, groups: int, plan: StatPlan, *, x1=None, eps=1e-5, count_eps=0.0, act=False, out=None):
+    """(x0|x1) -> act(groupnorm) with per-sample statistics over the row layout `plan` describes.  Statistics:
+    deterministic fp32 partials per (32-row segment, 4 channels) -- written by the producing tcgen05 GEMM's epilogue
+    when it was asked to (`gather_gemm(stats=plan)`), else by of_gn_stats -- summed in fixed order in fp64."""
     _lib.require_cuda(x0, x1, gamma, beta, out)
     rows = x0.shape[0]
+    assert rows == plan.rows, (rows, plan.rows)
     c0 = x0.shape[1]
     c1 = 0 if x1 is None else x1.shape[1]
     c = c0 + c1
+    if (c // groups) % 4 != 0 or c0 % 4 != 0:
+        raise NotImplementedError('group_norm: channels per group (%d) and the concat split (%d) must be multiples of 4'
+                                  % (c // groups, c0))
     dev = x0.device
-    sums = torch.zeros((batch, groups, 2), dtype=torch.float64, device=dev)
-    a1 = (ptr(x1), x1.stride(0), c1) if x1 is not None else (None, 0, 0)
-    sid = ptr(sample_id) if sample_id is not None else None
-    check(lib.of_gn_stats(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, batch, groups,
-                          dt(x0), ptr(sums), _next_direction() | _gn_general, stream()), 'of_gn_stats')
+    batch = plan.batch
+    p0 = _stats_of(x0, plan)
+    p1 = _stats_of(x1, plan) if x1 is not None else None
     scale = torch.empty((batch, c), dtype=torch.float32, device=dev)
     shift = torch.empty((batch, c), dtype=torch.float32, device=dev)
-    check(lib.of_gn_finalize(ptr(sums), ptr(rows_of_sample) if rows_of_sample is not None else None, rows_per_sample,
-                             ptr(gamma), ptr(beta), batch, c, groups, float(eps), float(count_eps), ptr(scale),
-                             ptr(shift), stream()), 'of_gn_finalize')
+    check(lib.of_gn_finalize(ptr(p0), c0, ptr(p1), c1, ptr(plan.sample_seg_off), ptr(plan.sample_seg_idx),
+                             ptr(plan.rows_of_sample), plan.rows_per_sample, ptr(gamma), ptr(beta), batch, groups,
+                             float(eps), float(count_eps), ptr(scale), ptr(shift), stream()), 'of_gn_finalize')
     if out is None:
         out = torch.empty((rows, c), dtype=x0.dtype, device=dev)
-    check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], sid, rows_per_sample, rows, ptr(scale),
-                          ptr(shift), _ACT[act], dt(x0), ptr(out), out.stride(0), _next_direction() | _gn_general, stream()),
-          'of_gn_apply')
+    a1 = (ptr(x1), x1.stride(0), c1) if x1 is not None else (None, 0, 0)
+    check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], ptr(plan.sample_id), plan.rows_per_sample, rows,
+                          ptr(scale), ptr(shift), _ACT[act], dt(x0), ptr(out), out.stride(0),
+                          _next_direction() | _gn_general, stream()), 'of_gn_apply')
     _trace('group_norm', out)
     return out
 

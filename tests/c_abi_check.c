@@ -13,6 +13,8 @@ int main(void) {
   printf("off_a_multi %zu\n", offsetof(of_gemm_args, a_multi));
   printf("off_nt_block %zu\n", offsetof(of_gemm_args, nt_block));
   printf("off_reverse %zu\n", offsetof(of_gemm_args, reverse));
+  printf("off_stat_out %zu\n", offsetof(of_gemm_args, stat_out));
+  printf("off_stat_rows_per_sample %zu\n", offsetof(of_gemm_args, stat_rows_per_sample));
   printf("sizeof_octree_levels %zu\n", sizeof(of_octree_levels));
   printf("off_nnum %zu\n", offsetof(of_octree_levels, nnum));
   printf("off_full_depth %zu\n", offsetof(of_octree_levels, full_depth));

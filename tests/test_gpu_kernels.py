@@ -175,6 +175,71 @@ def test_doctree_group_norm(dtype, d, c0, c1):
     assert relerr(y.float().cpu(), ref) < (2e-5 if dtype == torch.float32 else 8e-3)
 
 
+def _nan_parts(monkeypatch):
+    """every slot of a partial-statistics buffer must be written by its producer: start them as NaN"""
+    from octfusion_b200 import ops
+    orig = ops.StatPlan.new_part
+    monkeypatch.setattr(ops.StatPlan, 'new_part', lambda self, c: orig(self, c).fill_(float('nan')))
+
+
+@pytest.mark.parametrize('d,cin,cout,resid', [(6, 128, 128, True), (5, 128, 256, False), (4, 256, 512, False), (6, 64, 64, False)])
+def test_gemm_epilogue_statistics(monkeypatch, d, cin, cout, resid):
+    """The tcgen05 epilogue's group-norm partials (of_gemm_args.stat_out) against the stand-alone of_gn_stats pass over
+    the same output: same slots, sums equal up to the bf16 rounding of the stored tensor; the norm built on either is
+    the oracle's norm of the output.  3 ragged samples (chunks that straddle samples take the masked path)."""
+    from octfusion_b200 import ops
+    from octfusion_b200.modules import GraphConv, DualOctreeGroupNorm
+    _nan_parts(monkeypatch)
+    dg, _ = oracle_doctree(3, 5)
+    doc = product_doctree(3, 5)
+    plan = doc.plan[d]
+    n = plan.rows
+    conv = GraphConv(cin, cout, 7, 7, d - 1).to(DEV)
+    x = (_rand((n, cin), 3) * 1.5 + 0.3).to(DEV).bfloat16()
+    res = _rand((n, cout), 4).to(DEV).bfloat16() if resid else None
+    emb = _rand((3, cout), 5).to(DEV)
+    y = conv.run(x, plan, row_add=emb, row_add_idx=plan.batch_id, resid=res, stats=plan.stat)
+    st = getattr(y, '_of_stats', None)
+    assert st is not None and st.plan is plan.stat and st.part.shape == (plan.stat.n_seg, cout // 2)
+    fused = st.part.double().cpu()
+    assert torch.isfinite(fused).all()
+    alone = ops._stats_of(y.clone(), plan.stat).double().cpu()
+    assert torch.isfinite(alone).all()
+    # per segment the two differ by the bf16 rounding of <= 128 values; per sample (sum over its segments) by much less
+    off, idx = plan.stat.sample_seg_off.cpu().tolist(), plan.stat.sample_seg_idx.cpu().long()
+    for b in range(3):
+        sel = idx[off[b]:off[b + 1]]
+        fa, al = fused[sel].sum(0), alone[sel].sum(0)
+        assert float((fa - al).abs().max() / al.abs().max()) < 2e-3
+    gn = DualOctreeGroupNorm(cout).to(DEV)
+    a = gn.run(y, plan, 3, act=True).float().cpu()
+    ref = R.silu(R.doctree_group_norm(y.float().cpu(), dg.batch_id(d), 3, gn.weights.data.cpu(), gn.bias.data.cpu()))
+    assert relerr(a, ref) < 8e-3
+    # bit-reproducible: a second launch writes identical partials
+    y2 = conv.run(x, plan, row_add=emb, row_add_idx=plan.batch_id, resid=res, stats=plan.stat)
+    assert torch.equal(y2._of_stats.part, st.part) and torch.equal(y2, y)
+
+
+def test_gemm_epilogue_statistics_dense_small_samples(monkeypatch):
+    """dense layout with 8 rows per sample (T = 8 tokens of the cond config): four samples per 32-row chunk"""
+    from octfusion_b200 import ops
+    from octfusion_b200.modules import DenseTables, conv_nd, convnormalization
+    _nan_parts(monkeypatch)
+    b, c = 5, 128
+    t = DenseTables(b, DEV)
+    sp = t.stat_plan(1)
+    assert sp.n_seg == 5
+    lin = conv_nd(1, c, c, 1).to(DEV)
+    x = (_rand((b * 8, c), 1) + 0.2).to(DEV).bfloat16()
+    y = lin.run(x, stats=sp)
+    assert y._of_stats.part.shape == (5, c // 2) and torch.isfinite(y._of_stats.part).all()
+    norm = convnormalization(c).to(DEV)
+    a = norm.run(y, t, 1, act=True).float().cpu()
+    yy = y.float().cpu().reshape(b, 8, c).permute(0, 2, 1)                    # [B, C, T]
+    ref = R.silu(F.group_norm(yy, 32, norm.weight.data.cpu(), norm.bias.data.cpu(), 1e-5)).permute(0, 2, 1).reshape(b * 8, c)
+    assert relerr(a, ref) < 8e-3
+
+
 # ------------------------------------------------------------------------------------------------
 # attention / dense convolutions
 # ------------------------------------------------------------------------------------------------

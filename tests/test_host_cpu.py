@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), 'library does not export %s' % name
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.of_version() == 1
+    assert lib.of_version() == 2
 
 
 def test_argument_validation_without_gpu():
@@ -158,7 +158,7 @@ def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
     out = dict(l.split() for l in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.splitlines())
     g, o = _lib.GemmArgs, _lib.OctreeLevels
     assert int(out['sizeof_gemm_args']) == C.sizeof(g)
-    for f in ('tap_tab', 'w', 'out', 'M', 'a_multi', 'nt_block', 'reverse'):
+    for f in ('tap_tab', 'w', 'out', 'M', 'a_multi', 'nt_block', 'reverse', 'stat_out', 'stat_rows_per_sample'):
         assert int(out['off_' + f]) == getattr(g, f).offset, f
     assert int(out['sizeof_octree_levels']) == C.sizeof(o)
     assert int(out['off_nnum']) == o.nnum.offset and int(out['off_full_depth']) == o.full_depth.offset
@@ -178,3 +178,43 @@ def test_stage1_truncation_compares_in_float32_like_the_reference(steps):
     if steps >= 10:
         k = [i for i in range(steps) if float(times[i]) < 0.7 and not do_sign[i]]
         assert len(k) == 1          # the one step a double-precision compare would get wrong
+
+
+def test_stat_plan_segment_tables():
+    """ops.StatPlan (host/torch logic of the deterministic norm statistics): 32-row chunks split into per-sample
+    segments, against a brute-force walk; covers samples smaller than a chunk, one sample only, and the dense layout."""
+    from octfusion_b200.ops import StatPlan
+
+    def brute(bid):
+        rows = len(bid)
+        chunk_seg, seg_sample = [], []
+        for r in range(rows):
+            if r % 32 == 0:
+                chunk_seg.append(len(seg_sample))
+            if r % 32 == 0 or bid[r] != bid[r - 1]:
+                seg_sample.append(bid[r])
+        chunk_seg.append(len(seg_sample))
+        return chunk_seg, seg_sample
+
+    g = torch.Generator().manual_seed(0)
+    cases = []
+    # three "sections" (leaves of two depths + nodes), each batch-sorted, with tiny and empty samples
+    for counts in ([[5, 0, 40, 3], [70, 1, 1, 33], [100, 31, 64, 2]], [[4096], [100], [1000]], [[1, 1, 1]]):
+        bid = []
+        for sec in counts:
+            for b, n in enumerate(sec):
+                bid += [b] * n
+        cases.append((bid, len(counts[0])))
+    for bid, batch in cases:
+        sp = StatPlan(len(bid), batch, sample_id=torch.tensor(bid, dtype=torch.int32))
+        cs, ss = brute(bid)
+        assert sp.n_seg == len(ss) and sp.chunk_seg.tolist() == cs
+        off, idx = sp.sample_seg_off.tolist(), sp.sample_seg_idx.tolist()
+        assert off[0] == 0 and off[-1] == len(ss)
+        for b in range(batch):
+            mine = idx[off[b]:off[b + 1]]
+            assert mine == [k for k, s in enumerate(ss) if s == b]          # in row order
+    for rows_per_sample, batch in ((8, 5), (64, 3), (4096, 2)):
+        sp = StatPlan(rows_per_sample * batch, batch, rows_per_sample=rows_per_sample, device='cpu')
+        cs, ss = brute([r // rows_per_sample for r in range(rows_per_sample * batch)])
+        assert sp.chunk_seg.tolist() == cs and sp.n_seg == len(ss)

@@ -1,3 +1,15 @@
 #!/bin/bash
-timeout 250 python -m pytest tests/test_gpu_kernels.py -x -q 2>&1 | tail -2
-REPS=10 SHAPES="6,128,128;6,256,128;6,256,256;5,256,256;5,768,256;4,512,512" timeout 120 python tools/prof_conv.py 2>&1 | tail -6
+# round-2 experiment batch for the tcgen05 tap-gather GEMM: correctness first, then variants, then the timeline.
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+SH="6,128,128;6,256,128;6,384,128;6,128,256;5,256,256;5,128,256;5,768,256;5,512,512;4,512,512;4,256,256;6,64,128"
+echo "=== kernel tests"; timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q --timeout 300 2>&1 | tail -15
+for v in "MT=2 UNI=0" "MT=1 UNI=0" "MT=2 UNI=1"; do
+  set -- $v
+  echo "=== variant $v"
+  env OCTFUSION_TC_${1%%=*}=${1##*=} OCTFUSION_TC_${2%%=*}=${2##*=} SHAPES="$SH" REPS=10 timeout 600 python tools/prof_conv.py 2>&1 | tail -12
+done
+echo "=== timeline (default variant)"
+timeout 600 python tools/trace_tc.py "6,128,128;6,128,256;5,128,256;4,512,512" 2>&1 | tail -120
+echo "=== timeline UNI=1"
+OCTFUSION_TC_UNI=1 timeout 600 python tools/trace_tc.py "6,128,128;6,128,256" 2>&1 | tail -70
