@@ -110,9 +110,10 @@ typedef struct of_gemm_args {
    * values before they are rounded to bf16 (the statistics pass of the following DualOctreeGroupNorm,
    * modules.py:291-326, then never reads the tensor).  Rows are cut into 32-row chunks; a chunk is split into
    * SEGMENTS at every change of sample id; stat_chunk_seg [ceil(M/32)+1] is the exclusive prefix sum of segments
-   * per chunk (of_stat_plan_* in the Python layer builds it once per graph depth).  stat_out [n_segments, N/4, 2]
-   * fp32 receives (sum, sum of squares) per 4-channel granule of every segment -- one plain store per value, no
-   * atomics, fixed summation order: bit-reproducible.  Sample of row m: stat_sample[m], or m / stat_rows_per_sample
+   * per chunk (ops.StatPlan in the Python layer builds it once per graph depth).  stat_out [n_segments, N/G, 2]
+   * fp32 receives (sum, sum of squares) per G-channel granule of every segment, G = 4 when N %% 128 == 0 else 2 (a
+   * 64-channel norm has 2 channels per group) -- one plain store per value, no atomics, fixed summation order:
+   * bit-reproducible.  Sample of row m: stat_sample[m], or m / stat_rows_per_sample
    * when stat_sample is NULL.  Requires N % 32 == 0 and out_rows == NULL.  NULL = off.                        */
   float* stat_out;
   const int32_t* stat_chunk_seg;
@@ -147,19 +148,19 @@ int of_repack_weight(const float* src, int64_t s_tap, int64_t s_c, int64_t s_n,
  * x is the virtual concatenation (x0 | x1).  sample_id [rows] int32 (NULL => row / rows_per_sample).
  * Statistics are deterministic (no atomics): rows are cut into 32-row chunks, chunks into per-sample SEGMENTS
  * (see of_gemm_args.stat_out), and every segment owns one slot of a partial buffer.
- *   stats:    part [n_segments, C/4, 2] fp32 = (sum x, sum x^2) per 4-channel granule of each segment, one thread
+ *   stats:    part [n_segments, C/gran, 2] fp32 = (sum x, sum x^2) per granule of `gran` (2 or 4) channels of each segment, one thread
  *             per (chunk, channel vector), rows added in order.  The tcgen05 GEMM writes the same buffer from its
  *             epilogue (stat_out), in which case this pass is skipped.
  *   finalize: for sample b the segments sample_seg_idx[sample_seg_off[b] .. sample_seg_off[b+1]) are summed in that
  *             order in fp64 -> mean / variance per group -> scale/shift [B, C] fp32 (gamma, beta folded in).
  *             The normalised tensor is the concat (x0 | x1): part0 / part1 are the partial buffers of the two
- *             tensors (c1 = 0: one tensor).  C/groups must be a multiple of 4 and c0 % 4 == 0.
+ *             tensors with their granule widths (c1 = 0: one tensor).  C/groups and c0 must be multiples of the granules.
  *   apply:    y[r, c] = act(x[r, c] * scale[b, c] + shift[b, c])   act: 0 none, 1 SiLU, 2 GELU (erf)
  * ------------------------------------------------------------------------------------------ */
 int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                 const int32_t* chunk_seg, const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
-                int32_t dtype, float* part, void* stream);
-int of_gn_finalize(const float* part0, int32_t c0, const float* part1, int32_t c1,
+                int32_t dtype, int32_t gran, float* part, void* stream);
+int of_gn_finalize(const float* part0, int32_t c0, int32_t gran0, const float* part1, int32_t c1, int32_t gran1,
                    const int32_t* sample_seg_off, const int32_t* sample_seg_idx,
                    const int32_t* rows_of_sample, int32_t rows_per_sample,
                    const float* gamma, const float* beta, int32_t batch, int32_t groups, float eps,

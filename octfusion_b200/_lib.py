@@ -65,9 +65,9 @@ _PROTOS = {
     'of_pack_weight_tc_bytes': (_i64, [_i32, _i32, _i32, _i32]),
     'of_pack_weight_tc': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'of_repack_weight': (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
-    'of_gn_stats': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _i64, _i32, _vp, _vp]),
-    'of_gn_finalize': (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _f32, _f32, _vp, _vp,
-                                 _vp]),
+    'of_gn_stats': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
+    'of_gn_finalize': (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _f32, _f32,
+                                 _vp, _vp, _vp]),
     'of_gn_apply': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     'of_attention': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     'of_linear_small': (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),

@@ -71,6 +71,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe of a phase (true = the phase with this parity has completed)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug becomes a trap (an error the host sees), never a hung GPU.
 // variant for the long waits of the epilogue warps: back off between polls so that the four idle warps do not
 // compete with the producers for issue slots
@@ -258,24 +270,27 @@ struct TcParams {
   int cblocks;       // (c0+c1)/64
   int npad;          // N rounded up to 16 (rows per K block in the packed weight image)
   int m_tiles, n_tiles;   // m_tiles counts CTA tiles of 128*MT rows
-  int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA, 32 no tap-table reads
+  int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA, 32 no tap-table reads, 128 no next-stage probe
   unsigned long long* trace;   // of_tc_trace_set: per-role clock64 stamps of one CTA (diagnostics), or NULL
   int trace_cap, trace_block;
 };
 
-// trace regions (each trace_cap stamps): 0 MMA warp (3 per stage: B full, A full, issued), 1 weight loader (2 per stage:
+// trace regions (each trace_cap stamps): 0 MMA warp (5 per stage: stage ready, first-half MMAs issued, next stage
+// probed, second-half MMAs issued, committed), 1 weight loader (2 per stage:
 // slot free, issued), 2..5 producer groups (3 per slot: loop top, slot free, issued), 6 epilogue warp 0 (2 per tile)
 __device__ __forceinline__ void trace_put(const TcParams& p, int region, int& n, bool on) {
   if (on && n < p.trace_cap) p.trace[(size_t)region * p.trace_cap + n] = (unsigned long long)clock64();
   ++n;
 }
 
-// Sum of a[0..15] over the 32 lanes of the warp, one value per lane pair: afterwards a[0] of lane L holds the warp total
-// of the ORIGINAL a[(L >> 1) & 15].  Recursive halving: 8 + 4 + 2 + 1 + 1 = 16 shuffles (a plain butterfly needs 80).
-// The order of the additions is fixed, so the result is bit-reproducible.
-__device__ __forceinline__ void warp_reduce16(float (&a)[16], int lane) {
+// Sum of a[0..NV-1] (NV = 16 or 32) over the 32 lanes of the warp by recursive halving: NV = 16: 8+4+2+1+1 = 16 shuffles,
+// afterwards a[0] of lane L holds the warp total of the ORIGINAL a[(L >> 1) & 15]; NV = 32: 16+8+4+2+1 = 31 shuffles,
+// a[0] of lane L holds the total of the original a[L] (a plain butterfly needs 5 * NV).  The order of the additions
+// is fixed, so the result is bit-reproducible.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_vals(float (&a)[NV], int lane) {
 #pragma unroll
-  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+  for (int half = NV / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
     const bool up = (lane & bit) != 0;
 #pragma unroll
     for (int i = 0; i < half; ++i) {
@@ -284,7 +299,7 @@ __device__ __forceinline__ void warp_reduce16(float (&a)[16], int lane) {
       a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
     }
   }
-  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+  if (NV == 16) a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -428,26 +443,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           }
           if constexpr (CH == 32) {
             if (nseg > 0 && full) {
-              // (sum, sum of squares) of every 4-channel granule of my row; rows beyond M contribute zero
-              float a[16];
+              // (sum, sum of squares) of every GRAN-channel granule of my row; rows beyond M contribute zero.
+              // GRAN = 4 for the wide layers, 2 for N < 128 (a 64-channel norm has 2 channels per group).
+              constexpr int GRAN = BN >= 128 ? 4 : 2;
+              constexpr int NV = 2 * 32 / GRAN;
+              float a[NV];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float x0 = v[4 * q], x1 = v[4 * q + 1], x2 = v[4 * q + 2], x3 = v[4 * q + 3];
-                a[2 * q] = row_ok ? (x0 + x1) + (x2 + x3) : 0.0f;
-                a[2 * q + 1] = row_ok ? fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3) : 0.0f;
+              for (int q = 0; q < 32 / GRAN; ++q) {
+                float sv = 0.0f, qv = 0.0f;
+#pragma unroll
+                for (int e = 0; e < GRAN; ++e) { const float x = v[GRAN * q + e]; sv += x; qv = fmaf(x, x, qv); }
+                a[2 * q] = row_ok ? sv : 0.0f;
+                a[2 * q + 1] = row_ok ? qv : 0.0f;
               }
-              float* dst = g.stat_out + (int64_t)seg0 * (g.N >> 1) + (nb >> 1) + (lane >> 1);
+              const int nval = g.N / GRAN * 2;             // floats per segment slot
+              float* dst = g.stat_out + (int64_t)seg0 * nval + nb / GRAN * 2 + (NV == 16 ? (lane >> 1) : lane);
+              const bool writer = NV == 32 || (lane & 1) == 0;
               if (nseg == 1) {
-                warp_reduce16(a, lane);
-                if ((lane & 1) == 0) *dst = a[0];
+                warp_reduce_vals<NV>(a, lane);
+                if (writer) *dst = a[0];
               } else {
 #pragma unroll 1
                 for (int s = 0; s < nseg; ++s) {
-                  float t[16];
+                  float t[NV];
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) t[j] = (my_seg == s) ? a[j] : 0.0f;
-                  warp_reduce16(t, lane);
-                  if ((lane & 1) == 0) dst[(int64_t)s * (g.N >> 1)] = t[0];
+                  for (int j = 0; j < NV; ++j) t[j] = (my_seg == s) ? a[j] : 0.0f;
+                  warp_reduce_vals<NV>(t, lane);
+                  if (writer) dst[(int64_t)s * nval] = t[0];
                 }
               }
             }
@@ -460,47 +482,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     }
   } else if (warp == TC_EPI_WARPS) {
     // =========================== MMA issuer ===========================
-    // the whole warp walks the pipeline (all lanes wait on the barriers); one elected lane issues
+    // The whole warp walks the pipeline (all lanes wait on the barriers); one elected lane issues.  Issuing is nearly
+    // synchronous with execution (the tensor pipe accepts about one MMA ahead: profiles/tc_gather_experiments_r02.md),
+    // so every cycle this warp spends between two MMAs is a cycle the tensor pipe idles.  The full barrier(s) of the
+    // NEXT stage are therefore probed (mbarrier.test_wait, non-blocking) between the two halves of this stage's MMAs:
+    // the probe's latency overlaps the MMA in flight, and the blocking wait at the top of the next iteration is skipped
+    // when the probe found the stage ready (the normal case: the rings run ahead of the MMA warp).
     constexpr uint32_t idesc = make_idesc(BN);
     int stage = 0, bstage = 0;
     uint32_t phase = 0, bphase = 0;
     int it = 0, tn = 0;
+    bool ready = false;
+    const bool pipe = !(p.debug & 128);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       mbar_wait(bar_tempty + 8 * as, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
       for (int kb = 0; kb < p.num_kb; kb += KSUB) {
-        if constexpr (!UNI) mbar_wait(bar_bfull + 8 * bstage, bphase);
-        if (lane == 0) trace_put(p, 0, tn, tr);
-        mbar_wait(bar_full + 8 * stage, phase);
-        if (lane == 0) trace_put(p, 0, tn, tr);
+        if (!ready) {
+          if constexpr (!UNI) mbar_wait(bar_bfull + 8 * bstage, bphase);
+          mbar_wait(bar_full + 8 * stage, phase);
+        }
+        const bool el = elect_one();
+        if (el) trace_put(p, 0, tn, tr);
         const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
         const uint32_t b_addr = UNI ? a_addr + Cfg::A_BYTES : b_ring + bstage * Cfg::B_BYTES;
-        if (elect_one()) {
-          // descriptor low words: start address >> 4 (+2 per 32-byte K step), LBO = 1; the high word is constant
-          const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
-          const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
-          if (!(p.debug & 8)) {
+        // descriptor low words: start address >> 4 (+2 per 32-byte K step), LBO = 1; the high word is constant
+        const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
+        const bool two = KSUB > 1 && kb + 1 < p.num_kb;       // odd K-block count: the last stage is half full
+        auto issue = [&](int k0, int k1) {
 #pragma unroll
-            for (int j = 0; j < KSUB; ++j) {
-              if (j > 0 && kb + j >= p.num_kb) break;              // odd K-block count: the last stage is half full
+          for (int j = 0; j < KSUB; ++j) {
+            if (j > 0 && !two) break;
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k)
+            for (int k = k0; k < k1; ++k)
 #pragma unroll
-                for (int h = 0; h < MT; ++h)
-                  umma_bf16_lo(d_tmem + (uint32_t)(h * BN), a_lo + (j * MT + h) * (Cfg::A_SUB_BYTES >> 4) + 2 * k,
-                               b_lo + j * (Cfg::B_SUB_BYTES >> 4) + 2 * k, idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
-            }
+              for (int h = 0; h < MT; ++h)
+                umma_bf16_lo(d_tmem + (uint32_t)(h * BN), a_lo + (j * MT + h) * (Cfg::A_SUB_BYTES >> 4) + 2 * k,
+                             b_lo + j * (Cfg::B_SUB_BYTES >> 4) + 2 * k, idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
           }
+        };
+        if (el && !(p.debug & 8)) issue(0, TC_BK / 32);
+        if (el) trace_put(p, 0, tn, tr);
+        // ring position of the next stage (the rings run on across tile boundaries)
+        int nstage = stage + 1, nbstage = bstage + 1;
+        uint32_t nphase = phase, nbphase = bphase;
+        if (nstage == Cfg::A_STAGES) { nstage = 0; nphase ^= 1; }
+        if constexpr (!UNI) { if (nbstage == Cfg::B_STAGES) { nbstage = 0; nbphase ^= 1; } }
+        ready = false;
+        if (pipe) {
+          ready = mbar_test_wait(bar_full + 8 * nstage, nphase);
+          if constexpr (!UNI) ready = mbar_test_wait(bar_bfull + 8 * nbstage, nbphase) && ready;
+        }
+        if (el) {
+          trace_put(p, 0, tn, tr);
+          if (!(p.debug & 8)) issue(TC_BK / 32, TC_BK / 16);
+          trace_put(p, 0, tn, tr);
           umma_commit(bar_empty + 8 * stage);            // frees the stage when these MMAs retire
           if constexpr (!UNI) umma_commit(bar_bempty + 8 * bstage);
           if (kb + KSUB >= p.num_kb) umma_commit(bar_tfull + 8 * as);   // accumulators complete -> epilogue
+          trace_put(p, 0, tn, tr);
         }
         __syncwarp();
-        if (lane == 0) trace_put(p, 0, tn, tr);
-        if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
-        if constexpr (!UNI) { if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; } }
+        stage = nstage; phase = nphase;
+        if constexpr (!UNI) { bstage = nbstage; bphase = nbphase; }
       }
     }
   } else if (warp == TC_EPI_WARPS + 1) {

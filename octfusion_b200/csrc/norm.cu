@@ -90,7 +90,7 @@ __device__ __forceinline__ bool chunk_is_uniform(const GnSrc& s, int64_t r0, int
 // (sum, sum of squares) per 4-channel granule into the slot of the chunk's segment -- the layout the tcgen05 GEMM
 // epilogue produces (of_gemm_args.stat_out), so of_gn_finalize serves both.  A new segment starts at every change
 // of sample id inside the chunk.
-template <typename T, int V>
+template <typename T, int V, int GRAN>
 __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* __restrict__ chunk_seg, float* __restrict__ part) {
   const int C = s.c0 + s.c1;
   const int tpr = C / V;                                   // threads per chunk
@@ -102,18 +102,18 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* _
   const int64_t r1 = min(r0 + 32, s.rows);
   const T* base = cv < s.c0 ? reinterpret_cast<const T*>(s.x0) + cv : reinterpret_cast<const T*>(s.x1) + (cv - s.c0);
   const int64_t ld = cv < s.c0 ? s.ld0 : s.ld1;
-  constexpr int G = V / 4 > 0 ? V / 4 : 1;                 // granules per thread (V = 4 or 8)
+  constexpr int G = V / GRAN;                              // granules per thread (V = 4 or 8, GRAN = 2 or 4)
   float sum[G], sq[G];
 #pragma unroll
   for (int i = 0; i < G; ++i) { sum[i] = 0.0f; sq[i] = 0.0f; }
   int seg = chunk_seg[chunk];
-  const int half = C >> 1;                                 // floats per segment slot
+  const int half = C / GRAN * 2;                           // floats per segment slot
   auto sample_of = [&](int64_t r) { return s.sample_id ? s.sample_id[r] : (int)(r / s.rows_per_sample); };
   int cur = sample_of(r0);
   auto flush = [&]() {
 #pragma unroll
     for (int i = 0; i < G; ++i) {
-      *reinterpret_cast<float2*>(part + (int64_t)seg * half + ((cv >> 2) + i) * 2) = make_float2(sum[i], sq[i]);
+      *reinterpret_cast<float2*>(part + (int64_t)seg * half + (cv / GRAN + i) * 2) = make_float2(sum[i], sq[i]);
       sum[i] = 0.0f; sq[i] = 0.0f;
     }
   };
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* _
       const int b = sample_of(r + u);
       if (b != cur) { flush(); ++seg; cur = b; }
 #pragma unroll
-      for (int i = 0; i < V; ++i) { sum[i / 4] += f[u][i]; sq[i / 4] = fmaf(f[u][i], f[u][i], sq[i / 4]); }
+      for (int i = 0; i < V; ++i) { sum[i / GRAN] += f[u][i]; sq[i / GRAN] = fmaf(f[u][i], f[u][i], sq[i / GRAN]); }
     }
   }
   flush();
@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* _
 // One CTA per sample: partial slots of the sample's segments are summed in list order (fixed order, fp64), then the
 // group statistics and the [C] scale / shift rows of the sample are formed.
 //   smem: double red[slices][nval] | double tot[nval]
-__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ part0, int c0, const float* __restrict__ part1,
-                                                            int c1, const int32_t* __restrict__ seg_off,
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ part0, int c0, int gran0,
+                                                            const float* __restrict__ part1, int c1, int gran1,
+                                                            const int32_t* __restrict__ seg_off,
                                                             const int32_t* __restrict__ seg_idx,
                                                             const int32_t* __restrict__ rows_of_sample, int rows_per_sample,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -147,8 +148,8 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
   extern __shared__ double gn_sm[];
   const int b = blockIdx.x;
   const int C = c0 + c1;
-  const int nval = C >> 1;                                 // (sum, sumsq) x C/4 granules
-  const int h0 = c0 >> 1, h1 = c1 >> 1;
+  const int h0 = c0 / gran0 * 2, h1 = c1 > 0 ? c1 / gran1 * 2 : 0;   // floats per segment slot of the two buffers
+  const int nval = h0 + h1;
   const int slices = blockDim.x / nval;                    // >= 1 (checked on host)
   double* red = gn_sm;
   double* tot = gn_sm + (size_t)slices * nval;
@@ -188,8 +189,10 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
   const double inv = 1.0 / (n + (double)count_eps);      // modules.py:302: eps joins the COUNT
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
+    const int lo = g * cpg, hi = lo + cpg;                 // the group's channels: granules of x0 then of x1
     double S = 0.0, Q = 0.0;
-    for (int q = g * cpg / 4; q < (g + 1) * cpg / 4; ++q) { S += tot[2 * q]; Q += tot[2 * q + 1]; }
+    for (int ch = lo; ch < min(hi, c0); ch += gran0) { S += tot[ch / gran0 * 2]; Q += tot[ch / gran0 * 2 + 1]; }
+    for (int ch = max(lo, c0); ch < hi; ch += gran1) { S += tot[h0 + (ch - c0) / gran1 * 2]; Q += tot[h0 + (ch - c0) / gran1 * 2 + 1]; }
     const double m = S * inv;                              // modules.py:304
     double var = (Q - 2.0 * m * S + n * m * m) * inv;      // sum (x-m)^2 * inv_count, modules.py:308
     if (var < 0.0) var = 0.0;
@@ -303,7 +306,7 @@ static int check_src(const GnSrc& s, const char* who) {
 
 extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                            const int32_t* chunk_seg, const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
-                           int32_t dtype, float* part, void* stream) {
+                           int32_t dtype, int32_t gran, float* part, void* stream) {
   using namespace of;
   GnSrc s{x0, ld0, c0, x1, ld1, c1, sample_id, rows_per_sample, rows};
   int rc = check_src(s, "of_gn_stats");
@@ -311,6 +314,7 @@ extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* 
   const int C = c0 + c1;
   OF_REQUIRE(chunk_seg != nullptr && part != nullptr, "of_gn_stats: null chunk_seg/part");
   OF_REQUIRE(dtype == OF_F32 || dtype == OF_BF16, "of_gn_stats: bad dtype");
+  OF_REQUIRE(gran == 2 || gran == 4, "of_gn_stats: gran must be 2 or 4");
   const int esz = dtype == OF_F32 ? 4 : 2;
   int V = dtype == OF_F32 ? 4 : 8;
   if (V == 8 && !(C % 8 == 0 && vec_ok(x0, ld0, c0, 8, 2) && vec_ok(x1, ld1, c1, 8, 2))) V = 4;
@@ -322,34 +326,45 @@ extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* 
   const int64_t threads = chunks * (C / V);
   const int grid = (int)((threads + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == OF_F32) gn_stats_kernel<float, 4><<<grid, 256, 0, st>>>(s, chunk_seg, part);
-  else if (V == 8) gn_stats_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(s, chunk_seg, part);
-  else gn_stats_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(s, chunk_seg, part);
+#define OF_GN_STATS(T, VV)                                                                     \
+  do {                                                                                         \
+    if (gran == 4) gn_stats_kernel<T, VV, 4><<<grid, 256, 0, st>>>(s, chunk_seg, part);        \
+    else gn_stats_kernel<T, VV, 2><<<grid, 256, 0, st>>>(s, chunk_seg, part);                  \
+  } while (0)
+  if (dtype == OF_F32) OF_GN_STATS(float, 4);
+  else if (V == 8) OF_GN_STATS(__nv_bfloat16, 8);
+  else OF_GN_STATS(__nv_bfloat16, 4);
+#undef OF_GN_STATS
   OF_LAUNCH_CHECK("of_gn_stats");
   return OF_OK;
 }
 
-extern "C" int of_gn_finalize(const float* part0, int32_t c0, const float* part1, int32_t c1,
-                              const int32_t* sample_seg_off, const int32_t* sample_seg_idx,
+extern "C" int of_gn_finalize(const float* part0, int32_t c0, int32_t gran0, const float* part1, int32_t c1,
+                              int32_t gran1, const int32_t* sample_seg_off, const int32_t* sample_seg_idx,
                               const int32_t* rows_of_sample, int32_t rows_per_sample, const float* gamma,
                               const float* beta, int32_t batch, int32_t groups, float eps, float count_eps,
                               float* scale, float* shift, void* stream) {
   using namespace of;
   OF_REQUIRE(part0 && gamma && beta && scale && shift && sample_seg_off && sample_seg_idx, "of_gn_finalize: null pointer");
   OF_REQUIRE((part1 == nullptr) == (c1 == 0), "of_gn_finalize: part1/c1 inconsistent");
+  OF_REQUIRE((gran0 == 2 || gran0 == 4) && (c1 == 0 || gran1 == 2 || gran1 == 4), "of_gn_finalize: granules must be 2 or 4");
+  if (c1 == 0) gran1 = gran0;
   const int C = c0 + c1;
-  OF_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 4 == 0 && c0 % 4 == 0 && c1 % 4 == 0,
-             "of_gn_finalize: C=%d groups=%d c0=%d: channels per group and c0 must be multiples of 4", C, groups, c0);
+  OF_REQUIRE(groups > 0 && C % groups == 0, "of_gn_finalize: C=%d not divisible by groups=%d", C, groups);
+  const int cpg = C / groups;
+  OF_REQUIRE(cpg % gran0 == 0 && c0 % gran0 == 0 && (c1 == 0 || (cpg % gran1 == 0 && c1 % gran1 == 0 && c0 % gran1 == 0)),
+             "of_gn_finalize: C=%d groups=%d c0=%d: channels per group and c0 must be multiples of the granules (%d, %d)",
+             C, groups, c0, gran0, gran1);
   OF_REQUIRE(rows_of_sample != nullptr || rows_per_sample > 0, "of_gn_finalize: need a row count");
   OF_REQUIRE(batch > 0, "of_gn_finalize: bad batch");
-  const int nval = C / 2;
+  const int nval = c0 / gran0 * 2 + (c1 > 0 ? c1 / gran1 * 2 : 0);
   OF_REQUIRE(nval <= 1024, "of_gn_finalize: C=%d too wide", C);
   const int slices = 1024 / nval;
   const int threads = slices * nval;
   const size_t smem = ((size_t)slices * nval + nval) * sizeof(double);
   gn_finalize_kernel<<<batch, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      part0, c0, part1, c1, sample_seg_off, sample_seg_idx, rows_of_sample, rows_per_sample, gamma, beta, groups, eps,
-      count_eps, scale, shift);
+      part0, c0, gran0, part1, c1, gran1, sample_seg_off, sample_seg_idx, rows_of_sample, rows_per_sample, gamma, beta,
+      groups, eps, count_eps, scale, shift);
   OF_LAUNCH_CHECK("of_gn_finalize");
   return OF_OK;
 }

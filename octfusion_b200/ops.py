@@ -118,17 +118,23 @@ class StatPlan:
         off[1:] = torch.cumsum(cnt, 0).int()
         self.sample_seg_off = off
 
-    def new_part(self, channels: int):
-        """partial buffer [n_seg, channels/4, 2] fp32 (every slot is overwritten by its producer: no zeroing)"""
-        return torch.empty((max(self.n_seg, 1), channels // 2), dtype=torch.float32, device=self.chunk_seg.device)
+    def new_part(self, channels: int, gran: int):
+        """partial buffer [n_seg, channels/gran, 2] fp32 (every slot is overwritten by its producer: no zeroing)"""
+        return torch.empty((max(self.n_seg, 1), channels // gran * 2), dtype=torch.float32, device=self.chunk_seg.device)
+
+
+def tc_stat_gran(n: int) -> int:
+    """granule width of the statistics the tcgen05 epilogue writes for an N-column output (gemm_tc.cu: 4 for the
+    128/256-wide tiles, 2 below -- a 64-channel GroupNorm32 has 2 channels per group)"""
+    return 4 if n % 128 == 0 else 2
 
 
 class Stats:
-    """partial statistics of one tensor: (buffer, StatPlan); attached to GEMM outputs as `t._of_stats`."""
-    __slots__ = ('part', 'plan', 'channels')
+    """partial statistics of one tensor: (buffer, StatPlan, granule); attached to GEMM outputs as `t._of_stats`."""
+    __slots__ = ('part', 'plan', 'channels', 'gran')
 
-    def __init__(self, part, plan, channels):
-        self.part, self.plan, self.channels = part, plan, channels
+    def __init__(self, part, plan, channels, gran):
+        self.part, self.plan, self.channels, self.gran = part, plan, channels, gran
 
 
 _FUSE_STATS = os.environ.get('OCTFUSION_GN_FUSE', '1') != '0'     # 0: always run the stand-alone statistics pass
@@ -262,7 +268,7 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g.stat_out, g.stat_chunk_seg, g.stat_sample, g.stat_rows_per_sample = None, None, None, 0
     if (stats is not None and _FUSE_STATS and use_tc and n % 32 == 0 and out_rows is None and stats.rows == m
             and not g.out_f32):
-        st_obj = Stats(stats.new_part(n), stats, n)
+        st_obj = Stats(stats.new_part(n, tc_stat_gran(n)), stats, n, tc_stat_gran(n))
         g.stat_out, g.stat_chunk_seg = st_obj.part.data_ptr(), stats.chunk_seg.data_ptr()
         g.stat_sample = stats.sample_id.data_ptr() if stats.sample_id is not None else None
         g.stat_rows_per_sample = stats.rows_per_sample
@@ -322,15 +328,17 @@ _gn_general = 2 if os.environ.get('OCTFUSION_GN_GENERAL') == '1' else 0      # d
 _ACT = {False: 0, None: 0, True: 1, 'silu': 1, 'gelu': 2}
 
 
-def _stats_of(x, plan: StatPlan):
-    """partials of x under `plan`: those its producing GEMM attached, else one stand-alone statistics pass"""
+def _stats_of(x, plan: StatPlan, cpg: int):
+    """(partials, granule) of x under `plan`: those its producing GEMM attached when their granule divides the
+    channels-per-group `cpg`, else one stand-alone statistics pass"""
     st = getattr(x, '_of_stats', None)
-    if st is not None and st.plan is plan and st.channels == x.shape[1]:
-        return st.part
-    part = plan.new_part(x.shape[1])
+    if st is not None and st.plan is plan and st.channels == x.shape[1] and cpg % st.gran == 0:
+        return st.part, st.gran
+    gran = 4 if cpg % 4 == 0 else 2
+    part = plan.new_part(x.shape[1], gran)
     check(lib.of_gn_stats(ptr(x), x.stride(0), x.shape[1], None, 0, 0, ptr(plan.chunk_seg), ptr(plan.sample_id),
-                          plan.rows_per_sample, x.shape[0], dt(x), ptr(part), stream()), 'of_gn_stats')
-    return part
+                          plan.rows_per_sample, x.shape[0], dt(x), gran, ptr(part), stream()), 'of_gn_stats')
+    return part, gran
 
 
 def group_norm(x0, gamma, beta, groups: int, plan: StatPlan, *, x1=None, eps=1e-5, count_eps=0.0, act=False, out=None):
@@ -343,16 +351,17 @@ def group_norm(x0, gamma, beta, groups: int, plan: StatPlan, *, x1=None, eps=1e-
     c0 = x0.shape[1]
     c1 = 0 if x1 is None else x1.shape[1]
     c = c0 + c1
-    if (c // groups) % 4 != 0 or c0 % 4 != 0:
-        raise NotImplementedError('group_norm: channels per group (%d) and the concat split (%d) must be multiples of 4'
-                                  % (c // groups, c0))
+    cpg = c // groups
+    if cpg % 2 != 0 or c0 % 4 != 0 or c1 % 4 != 0:
+        raise NotImplementedError('group_norm: channels per group (%d) must be even and the concat split (%d | %d) '
+                                  'multiples of 4' % (cpg, c0, c1))
     dev = x0.device
     batch = plan.batch
-    p0 = _stats_of(x0, plan)
-    p1 = _stats_of(x1, plan) if x1 is not None else None
+    p0, g0 = _stats_of(x0, plan, cpg)
+    p1, g1 = _stats_of(x1, plan, cpg) if x1 is not None else (None, g0)
     scale = torch.empty((batch, c), dtype=torch.float32, device=dev)
     shift = torch.empty((batch, c), dtype=torch.float32, device=dev)
-    check(lib.of_gn_finalize(ptr(p0), c0, ptr(p1), c1, ptr(plan.sample_seg_off), ptr(plan.sample_seg_idx),
+    check(lib.of_gn_finalize(ptr(p0), c0, g0, ptr(p1), c1, g1, ptr(plan.sample_seg_off), ptr(plan.sample_seg_idx),
                              ptr(plan.rows_of_sample), plan.rows_per_sample, ptr(gamma), ptr(beta), batch, groups,
                              float(eps), float(count_eps), ptr(scale), ptr(shift), stream()), 'of_gn_finalize')
     if out is None:

@@ -61,3 +61,12 @@ def synth_splits(batch_size: int, seed: int = 0, full_depth: int = 4, halfwidth=
         m5 = _in_shell(x5, y5, z5, full_depth + 1, centre, axes, halfwidth[1])
         lab5.append(m5.long())
     return torch.cat(lab4), torch.cat(lab5)
+
+
+def slice_splits(label_fd, label_fd1, lo: int, hi: int, full_depth: int = 4):
+    """labels of shapes [lo, hi) out of a synth_splits(B, ...) result (batch sharding: every rank generates the same B
+    shapes and keeps its contiguous block)."""
+    nfull = 8 ** full_depth
+    per = label_fd.view(-1, nfull).sum(1) * 8                  # depth-(fd+1) nodes per shape
+    off = torch.cat([torch.zeros(1, dtype=per.dtype), torch.cumsum(per, 0)])
+    return label_fd[lo * nfull: hi * nfull], label_fd1[int(off[lo]): int(off[hi])]

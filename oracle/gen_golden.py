@@ -95,10 +95,28 @@ def unet_fixture(ref, name):
     print(name, 'out absmax', float(y.abs().max()), 'N', d.total_num)
 
 
+def state_shapes(ref):
+    """state_dict shapes of the unmodified reference nets -> tests/golden/state_shapes.json (lets bench.py's CPU arm
+    build seeded weights on hosts without the reference tree and without importing the product package)."""
+    import json
+    out = {}
+    for name in ('uncond', 'uncond8', 'cond'):
+        cfg = UNET_CASES[name][0]
+        with torch.device('meta'):
+            net = ref.union.UNet3DModel('hr', **cfg)
+        out[name] = {k: list(v.shape) for k, v in net.state_dict().items()}
+    with open(os.path.join(OUT, 'state_shapes.json'), 'w') as f:
+        json.dump(out, f)
+    print('state_shapes.json', {k: len(v) for k, v in out.items()})
+
+
 def main():
     ref = ref_import.load()
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
+    if 'shapes' in sys.argv[1:]:
+        state_shapes(ref)
+        return
     only = [a for a in sys.argv[1:] if a in UNET_CASES]
     if only:                                   # python -m oracle.gen_golden uncond8 cond_b4: just these fixtures
         for name in only:
@@ -148,6 +166,7 @@ def main():
     # 4. full U-Net forwards (weights from the shared seeded_state_dict)
     for name in UNET_CASES:
         unet_fixture(ref, name)
+    state_shapes(ref)
     # 5. GraphVAE decoder: decode_code(update_octree=True) of the unmodified reference
     import importlib
     from tests import util as U

@@ -179,7 +179,7 @@ def _nan_parts(monkeypatch):
     """every slot of a partial-statistics buffer must be written by its producer: start them as NaN"""
     from octfusion_b200 import ops
     orig = ops.StatPlan.new_part
-    monkeypatch.setattr(ops.StatPlan, 'new_part', lambda self, c: orig(self, c).fill_(float('nan')))
+    monkeypatch.setattr(ops.StatPlan, 'new_part', lambda self, c, g: orig(self, c, g).fill_(float('nan')))
 
 
 @pytest.mark.parametrize('d,cin,cout,resid', [(6, 128, 128, True), (5, 128, 256, False), (4, 256, 512, False), (6, 64, 64, False)])
@@ -200,10 +200,12 @@ def test_gemm_epilogue_statistics(monkeypatch, d, cin, cout, resid):
     emb = _rand((3, cout), 5).to(DEV)
     y = conv.run(x, plan, row_add=emb, row_add_idx=plan.batch_id, resid=res, stats=plan.stat)
     st = getattr(y, '_of_stats', None)
-    assert st is not None and st.plan is plan.stat and st.part.shape == (plan.stat.n_seg, cout // 2)
+    assert st is not None and st.plan is plan.stat and st.part.shape == (plan.stat.n_seg, cout // st.gran * 2)
     fused = st.part.double().cpu()
     assert torch.isfinite(fused).all()
-    alone = ops._stats_of(y.clone(), plan.stat).double().cpu()
+    alone, ga = ops._stats_of(y.clone(), plan.stat, st.gran)
+    assert ga == st.gran
+    alone = alone.double().cpu()
     assert torch.isfinite(alone).all()
     # per segment the two differ by the bf16 rounding of <= 128 values; per sample (sum over its segments) by much less
     off, idx = plan.stat.sample_seg_off.cpu().tolist(), plan.stat.sample_seg_idx.cpu().long()
@@ -232,7 +234,7 @@ def test_gemm_epilogue_statistics_dense_small_samples(monkeypatch):
     lin = conv_nd(1, c, c, 1).to(DEV)
     x = (_rand((b * 8, c), 1) + 0.2).to(DEV).bfloat16()
     y = lin.run(x, stats=sp)
-    assert y._of_stats.part.shape == (5, c // 2) and torch.isfinite(y._of_stats.part).all()
+    assert y._of_stats.part.shape == (5, c // 2) and y._of_stats.gran == 4 and torch.isfinite(y._of_stats.part).all()
     norm = convnormalization(c).to(DEV)
     a = norm.run(y, t, 1, act=True).float().cpu()
     yy = y.float().cpu().reshape(b, 8, c).permute(0, 2, 1)                    # [B, C, T]

@@ -1,6 +1,7 @@
 """Pipeline timeline of ONE CTA of the tcgen05 tap-gather GEMM (of_tc_trace_set): where each warp role waits.
 usage: python tools/trace_tc.py "6,128,128;6,256,256" [block]      (depth, cin, cout per layer; env BATCH)
-Regions (clock64 stamps, include/octfusion_b200.h): 0 MMA warp (per stage: B full, A full, issued), 1 weight loader
+Regions (clock64 stamps, include/octfusion_b200.h): 0 MMA warp (per stage: ready, half the MMAs issued, next stage
+probed, all MMAs issued, committed), 1 weight loader
 (slot free, issued), 2..5 producer groups (loop top, slot free, issued), 6 epilogue warp 0 (accumulator full, drained)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,7 +13,7 @@ from octfusion_b200.synth import synth_splits
 from octfusion_b200.modules import GraphConv
 
 B = int(os.environ.get('BATCH', 32))
-CAP = 6144
+CAP = 8192
 shapes = [tuple(int(v) for v in sh.split(',')) for sh in (sys.argv[1] if len(sys.argv) > 1 else '6,128,128').split(';')]
 block = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 l4, l5 = synth_splits(B, 0)
@@ -43,13 +44,15 @@ for d, cin, cout in shapes:
     t = buf.cpu().numpy()
     k = 7 * (cin + d - 1)
     print('== depth %d rows %d K %d N %d: %.1f us (traced launch), block %d' % (d, n, k, cout, e0.elapsed_time(e1) * 1e3, block))
-    m = t[0][t[0] > 0]; m = m[: len(m) // 3 * 3].reshape(-1, 3)
+    m = t[0][t[0] > 0]; m = m[: len(m) // 5 * 5].reshape(-1, 5)
     if len(m) > 2:
-        print('  MMA warp: %d stages, span %d clk' % (len(m), m[-1, 2] - m[0, 0]))
-        stat('wait B full (from prev issue)', m[1:, 0] - m[:-1, 2])
-        stat('wait A full', m[:, 1] - m[:, 0])
-        stat('issue MMAs + commits', m[:, 2] - m[:, 1])
-        stat('stage period', m[1:, 2] - m[:-1, 2])
+        print('  MMA warp: %d stages, span %d clk' % (len(m), m[-1, 4] - m[0, 0]))
+        stat('stage ready (from prev commit)', m[1:, 0] - m[:-1, 4])
+        stat('issue first-half MMAs', m[:, 1] - m[:, 0])
+        stat('probe next stage', m[:, 2] - m[:, 1])
+        stat('issue second-half MMAs', m[:, 3] - m[:, 2])
+        stat('commits', m[:, 4] - m[:, 3])
+        stat('stage period', m[1:, 4] - m[:-1, 4])
     w = t[1][t[1] > 0]; w = w[: len(w) // 2 * 2].reshape(-1, 2)
     if len(w) > 2:
         print('  weight loader:')
