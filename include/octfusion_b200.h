@@ -284,6 +284,14 @@ int of_graph_edges(const int32_t* tap_tab, const int32_t* tap_extra, int64_t slo
                    const int32_t* slot_off, int64_t* edge_row, int64_t* edge_col, int64_t* edge_dir,
                    void* stream);
 
+/* 3^3 neighbour table of the third-party operator ocnn.nn.OctreeConv (BASELINE.json configs[0]; the reference never
+ * calls it -- SURVEY.md section 0 -- its semantics are restated from ocnn-pytorch 2.2.x, SURVEY.md Appendix B: parity
+ * is UNPINNED at the ocnn boundary): neigh [nnum[depth], 27] int32, entry (dx+1)*9 + (dy+1)*3 + (dz+1) = index within
+ * `depth` of the node at (x+dx, y+dy, z+dz), -1 outside the volume or where no node exists.  The table is a tap table
+ * of the tap-gather GEMM (taps = 27, weights [27, Cin, Cout] flattened to [27*Cin, Cout]).  Only keys / children / nnum
+ * / full_depth / depth / batch of `oct` are read. */
+int of_octree_neigh27(const of_octree_levels* oct, int32_t depth, int32_t* neigh, void* stream);
+
 /* Dense voxel neighbour tables in Morton order for the LR middle U-Net (graph_unet_lr.py):
  * mode 0: 3^3 conv, same resolution `res_log2`        (Conv3d padding=1, modules.py:493-502)
  * mode 1: 3^3 stride-2 conv, out res = in res / 2      (ConvDownsample, modules.py:80-95)

@@ -92,6 +92,7 @@ _PROTOS = {
     'of_graph_edge_count': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'of_graph_edges': (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     'of_dense_tap_table': (C.c_int, [_i32, _i32, _i32, _vp, _vp]),
+    'of_octree_neigh27': (C.c_int, [C.POINTER(OctreeLevels), _i32, _vp, _vp]),
     'of_mpu_eval': (C.c_int, [C.POINTER(OctreeLevels), _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
 }
 

@@ -9,13 +9,14 @@
 // The im2col buffer is never written to HBM: gather warps build each [128 x 64] bf16 A tile
 // directly in shared memory, in the 128-byte-swizzled K-major layout tcgen05.mma reads.
 //
-// One persistent CTA per SM, 448 threads, warp-specialised:
+// One persistent CTA per SM, 480 threads, warp-specialised:
 //   warps 0-3   epilogue: tcgen05.ld of the fp32 accumulator, +bias/+emb[batch]/+residual, store; optionally the
 //               group-norm partial statistics of the tile (warp-shuffle reduction, one write per 32-row chunk --
 //               no atomics, bit-reproducible): the statistics pass of the following DualOctreeGroupNorm
 //               (modules.py:291-326) never reads the tensor again
-//   warp  4     MMA issuer (whole warp walks the pipeline, elect.sync lane issues): tcgen05.mma 128 x BN x 16,
-//               tcgen05.commit releases the shared-memory stages
+//   warp  4     MMA issuer (elect.sync lane issues): tcgen05.mma 128 x BN x 16, tcgen05.commit releases the
+//               shared-memory stages; it never waits on an mbarrier for operands -- warp 14 (scout) does, and publishes
+//               the count of ready stages in shared memory
 //   warp  5     weight loader: cp.async.bulk (TMA 1-D) of pre-swizzled [BN x 64] tiles
 //   warps 6-13  gather producers (4 groups x 2 warps, each group owns every 4th 16 KB sub-tile):
 //               tap table -> sixteen 16-byte cp.async (LDGSTS) per thread straight into the swizzled A stage,
@@ -42,7 +43,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
 constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;   // 448
+constexpr int TC_SCOUT_WARP = TC_EPI_WARPS + 2 + TC_PROD_WARPS;        // warp 14: watches the full barriers for the MMA warp
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS + 1) * 32;   // 480
 constexpr int TC_MAX_TAPS = 27;
 constexpr int TC_GROUPS = 4;                // producer groups of 2 warps
 
@@ -70,6 +72,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
+}
+__device__ __forceinline__ void st_release_cta(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
 }
 // non-blocking probe of a phase (true = the phase with this parity has completed)
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
@@ -270,13 +280,12 @@ struct TcParams {
   int cblocks;       // (c0+c1)/64
   int npad;          // N rounded up to 16 (rows per K block in the packed weight image)
   int m_tiles, n_tiles;   // m_tiles counts CTA tiles of 128*MT rows
-  int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA, 32 no tap-table reads, 128 no next-stage probe
+  int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA, 32 no tap-table reads
   unsigned long long* trace;   // of_tc_trace_set: per-role clock64 stamps of one CTA (diagnostics), or NULL
   int trace_cap, trace_block;
 };
 
-// trace regions (each trace_cap stamps): 0 MMA warp (5 per stage: stage ready, first-half MMAs issued, next stage
-// probed, second-half MMAs issued, committed), 1 weight loader (2 per stage:
+// trace regions (each trace_cap stamps): 0 MMA warp (3 per stage: stage ready, MMAs issued, committed), 1 weight loader (2 per stage:
 // slot free, issued), 2..5 producer groups (3 per slot: loop top, slot free, issued), 6 epilogue warp 0 (2 per tile)
 __device__ __forceinline__ void trace_put(const TcParams& p, int region, int& n, bool on) {
   if (on && n < p.trace_cap) p.trace[(size_t)region * p.trace_cap + n] = (unsigned long long)clock64();
@@ -320,6 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   const uint32_t bar_bfull = aux + 256, bar_bempty = aux + 288;
   const uint32_t bar_tfull = aux + 320, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t ready_ctr = aux + 368;                  // stages whose operands have landed (written by the scout warp)
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::RING_BYTES + 352);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -342,6 +352,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS * 32);
     }
+    st_release_cta(ready_ctr, 0u);
     fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -385,13 +396,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           }
         }
         constexpr int CH = BN >= 32 ? 32 : 16;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += CH) {
-          uint32_t acc[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((as * MT + h) * BN + c0);
-          if (CH == 32) { OF_TMEM_LD32(taddr, acc); } else { OF_TMEM_LD16(taddr, acc); }
-          tmem_ld_wait();
-          if (p.debug & 4) continue;
+        // one 32-column chunk of my row: accumulators -> (+bias, +emb, +residual) -> store (+ norm statistics)
+        auto process = [&](uint32_t (&acc)[32], int c0) {
           const int nb = n0 + c0;
           float v[32];
 #pragma unroll
@@ -474,6 +480,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
               }
             }
           }
+        };
+        // two TMEM loads in flight per iteration: the epilogue is latency-bound (tcgen05.ld -> wait -> stores), not
+        // issue-bound, and with the MMA warp no longer waiting on barriers a short-K tile leaves it ~8k cycles
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 2 * CH) {
+          uint32_t accA[32], accB[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((as * MT + h) * BN + c0);
+          const bool pair = c0 + CH < BN;
+          if (CH == 32) { OF_TMEM_LD32(taddr, accA); if (pair) { OF_TMEM_LD32(taddr + CH, accB); } }
+          else { OF_TMEM_LD16(taddr, accA); if (pair) { OF_TMEM_LD16(taddr + CH, accB); } }
+          tmem_ld_wait();
+          if (p.debug & 4) continue;
+          process(accA, c0);
+          if (pair) process(accB, c0 + CH);
         }
       }
       tc_fence_before();
@@ -482,63 +502,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     }
   } else if (warp == TC_EPI_WARPS) {
     // =========================== MMA issuer ===========================
-    // The whole warp walks the pipeline (all lanes wait on the barriers); one elected lane issues.  Issuing is nearly
-    // synchronous with execution (the tensor pipe accepts about one MMA ahead: profiles/tc_gather_experiments_r02.md),
-    // so every cycle this warp spends between two MMAs is a cycle the tensor pipe idles.  The full barrier(s) of the
-    // NEXT stage are therefore probed (mbarrier.test_wait, non-blocking) between the two halves of this stage's MMAs:
-    // the probe's latency overlaps the MMA in flight, and the blocking wait at the top of the next iteration is skipped
-    // when the probe found the stage ready (the normal case: the rings run ahead of the MMA warp).
+    // Issuing is nearly synchronous with execution (the tensor pipe accepts only a few MMAs ahead), so every cycle this
+    // warp spends between two MMAs is a cycle the tensor pipe idles; an mbarrier wait costs 100-300 cycles even when the
+    // phase has long completed (profiles/tc_gather_experiments_r02.md).  The waits on the full barriers are therefore
+    // done by the scout warp, which publishes the number of stages whose operands have landed in a shared-memory
+    // counter; this warp only compares its stage index with a cached copy of the counter (one ld.acquire when the copy
+    // runs out), issues the stage's MMAs from converged code (elect.sync) and commits.
     constexpr uint32_t idesc = make_idesc(BN);
     int stage = 0, bstage = 0;
-    uint32_t phase = 0, bphase = 0;
     int it = 0, tn = 0;
-    bool ready = false;
-    const bool pipe = !(p.debug & 128);
+    uint32_t nstage = 0, avail = 0;                          // stages consumed / stages known to be ready
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       mbar_wait(bar_tempty + 8 * as, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
-      for (int kb = 0; kb < p.num_kb; kb += KSUB) {
-        if (!ready) {
-          if constexpr (!UNI) mbar_wait(bar_bfull + 8 * bstage, bphase);
-          mbar_wait(bar_full + 8 * stage, phase);
+      for (int kb = 0; kb < p.num_kb; kb += KSUB, ++nstage) {
+        if (avail <= nstage) {
+          const long long t0 = clock64();
+          while ((avail = ld_acquire_cta(ready_ctr)) <= nstage) {
+            if (clock64() - t0 > 4000000000ll) {
+              printf("octfusion_b200 gemm_tc: MMA warp starved (block %d stage %u ready %u)\n", (int)blockIdx.x, nstage, avail);
+              __trap();
+            }
+          }
         }
-        const bool el = elect_one();
-        if (el) trace_put(p, 0, tn, tr);
         const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
         const uint32_t b_addr = UNI ? a_addr + Cfg::A_BYTES : b_ring + bstage * Cfg::B_BYTES;
         // descriptor low words: start address >> 4 (+2 per 32-byte K step), LBO = 1; the high word is constant
         const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
         const uint32_t b_lo = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
         const bool two = KSUB > 1 && kb + 1 < p.num_kb;       // odd K-block count: the last stage is half full
-        auto issue = [&](int k0, int k1) {
-#pragma unroll
-          for (int j = 0; j < KSUB; ++j) {
-            if (j > 0 && !two) break;
-#pragma unroll
-            for (int k = k0; k < k1; ++k)
-#pragma unroll
-              for (int h = 0; h < MT; ++h)
-                umma_bf16_lo(d_tmem + (uint32_t)(h * BN), a_lo + (j * MT + h) * (Cfg::A_SUB_BYTES >> 4) + 2 * k,
-                             b_lo + j * (Cfg::B_SUB_BYTES >> 4) + 2 * k, idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
-          }
-        };
-        if (el && !(p.debug & 8)) issue(0, TC_BK / 32);
-        if (el) trace_put(p, 0, tn, tr);
-        // ring position of the next stage (the rings run on across tile boundaries)
-        int nstage = stage + 1, nbstage = bstage + 1;
-        uint32_t nphase = phase, nbphase = bphase;
-        if (nstage == Cfg::A_STAGES) { nstage = 0; nphase ^= 1; }
-        if constexpr (!UNI) { if (nbstage == Cfg::B_STAGES) { nbstage = 0; nbphase ^= 1; } }
-        ready = false;
-        if (pipe) {
-          ready = mbar_test_wait(bar_full + 8 * nstage, nphase);
-          if constexpr (!UNI) ready = mbar_test_wait(bar_bfull + 8 * nbstage, nbphase) && ready;
-        }
-        if (el) {
+        if (elect_one()) {
           trace_put(p, 0, tn, tr);
-          if (!(p.debug & 8)) issue(TC_BK / 32, TC_BK / 16);
+          if (!(p.debug & 8)) {
+#pragma unroll
+            for (int j = 0; j < KSUB; ++j) {
+              if (j > 0 && !two) break;
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+#pragma unroll
+                for (int h = 0; h < MT; ++h)
+                  umma_bf16_lo(d_tmem + (uint32_t)(h * BN), a_lo + (j * MT + h) * (Cfg::A_SUB_BYTES >> 4) + 2 * k,
+                               b_lo + j * (Cfg::B_SUB_BYTES >> 4) + 2 * k, idesc, (kb + j > 0 || k > 0) ? 1u : 0u);
+            }
+          }
           trace_put(p, 0, tn, tr);
           umma_commit(bar_empty + 8 * stage);            // frees the stage when these MMAs retire
           if constexpr (!UNI) umma_commit(bar_bempty + 8 * bstage);
@@ -546,8 +554,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           trace_put(p, 0, tn, tr);
         }
         __syncwarp();
-        stage = nstage; phase = nphase;
-        if constexpr (!UNI) { bstage = nbstage; bphase = nbphase; }
+        if (++stage == Cfg::A_STAGES) stage = 0;
+        if constexpr (!UNI) { if (++bstage == Cfg::B_STAGES) bstage = 0; }
+      }
+    }
+  } else if (warp == TC_SCOUT_WARP) {
+    // =========================== scout ===========================
+    // waits on the full barriers in consumption order and publishes the count of ready stages (see the MMA issuer)
+    int stage = 0, bstage = 0;
+    uint32_t phase = 0, bphase = 0, n = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.num_kb; kb += KSUB) {
+        if constexpr (!UNI) mbar_wait(bar_bfull + 8 * bstage, bphase);
+        mbar_wait(bar_full + 8 * stage, phase);
+        ++n;
+        if (lane == 0) st_release_cta(ready_ctr, n);
+        __syncwarp();
+        if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
+        if constexpr (!UNI) { if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; } }
       }
     }
   } else if (warp == TC_EPI_WARPS + 1) {
@@ -577,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp < TC_SCOUT_WARP) {
     // =========================== gather producers ===========================
     // 4 independent groups of 2 warps; group g produces the 16 KB sub-tiles whose running index is = g mod 4, so 4
     // sub-tiles (64 KB of gathers) are in flight per SM and the memory latency of one is hidden behind the other three.

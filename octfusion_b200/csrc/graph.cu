@@ -547,6 +547,57 @@ extern "C" int of_graph_fill(const of_octree_levels* oct, int32_t D, const int32
   return OF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3^3 neighbour table of ocnn.nn.OctreeConv (`octree.get_neigh(depth, '333')`; BASELINE.json configs[0]): for every
+// octree node of `depth` the index (within that depth) of the node at (x+dx, y+dy, z+dz), tap = (dx+1)*9 + (dy+1)*3 +
+// (dz+1), or -1 when that cell is outside the volume or does not exist (its parent is empty).  One warp per node,
+// one lane per tap: the cell is located top-down through `children` from the full layer (no key hashing / search).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) octree_neigh27_kernel(GraphCtx g, int d, int32_t* __restrict__ out) {
+  const int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int tap = threadIdx.x & 31;
+  if (node >= g.nnum[d] || tap >= 27) return;
+  int x, y, z, b;
+  key_decode(g.keys[d][node], d, x, y, z, b);
+  const int nx = x + tap / 9 - 1, ny = y + (tap / 3) % 3 - 1, nz = z + tap % 3 - 1;
+  const int lim = 1 << d;
+  int res = -1;
+  if (nx >= 0 && ny >= 0 && nz >= 0 && nx < lim && ny < lim && nz < lim) {
+    int cd = g.fd;
+    int ci = (int)(((int64_t)b << (3 * g.fd)) + morton3(nx >> (d - g.fd), ny >> (d - g.fd), nz >> (d - g.fd), g.fd));
+    while (cd < d) {
+      const int c = g.children[cd][ci];
+      if (c < 0) break;
+      const int sh = d - cd - 1;
+      ci = 8 * c + ((((nx >> sh) & 1) << 2) | (((ny >> sh) & 1) << 1) | ((nz >> sh) & 1));
+      ++cd;
+    }
+    if (cd == d) res = ci;
+  }
+  out[node * 27 + tap] = res;
+}
+
+extern "C" int of_octree_neigh27(const of_octree_levels* oct, int32_t depth, int32_t* neigh, void* stream) {
+  using namespace of;
+  OF_REQUIRE(oct != nullptr && neigh != nullptr, "of_octree_neigh27: null pointer");
+  OF_REQUIRE(oct->full_depth >= 1 && depth >= oct->full_depth && depth <= oct->depth && depth < 16,
+             "of_octree_neigh27: depth %d outside [full_depth %d, depth %d]", depth, oct->full_depth, oct->depth);
+  GraphCtx g;
+  for (int d = 0; d < 16; ++d) {
+    g.keys[d] = oct->keys[d]; g.children[d] = oct->children[d]; g.leaf_rank[d] = nullptr;
+    g.nnum[d] = oct->nnum[d]; g.row_base[d] = 0;
+  }
+  g.fd = oct->full_depth; g.depth = oct->depth; g.D = depth; g.batch = oct->batch;
+  for (int d = g.fd; d <= depth; ++d)
+    OF_REQUIRE(oct->keys[d] && oct->children[d] && oct->nnum[d] >= 0, "of_octree_neigh27: level %d missing", d);
+  const int64_t n = oct->nnum[depth];
+  if (n == 0) return OF_OK;
+  const int64_t threads = n * 32;
+  octree_neigh27_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, depth, neigh);
+  OF_LAUNCH_CHECK("of_octree_neigh27");
+  return OF_OK;
+}
+
 extern "C" int of_graph_edge_count(const int32_t* tap_tab, const int32_t* tap_extra, int64_t slots, int32_t* per_slot,
                                    void* stream) {
   OF_REQUIRE(tap_tab && per_slot && slots >= 0, "of_graph_edge_count: bad arguments");

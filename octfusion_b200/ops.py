@@ -370,6 +370,9 @@ def group_norm(x0, gamma, beta, groups: int, plan: StatPlan, *, x1=None, eps=1e-
     check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], ptr(plan.sample_id), plan.rows_per_sample, rows,
                           ptr(scale), ptr(shift), _ACT[act], dt(x0), ptr(out), out.stride(0),
                           _next_direction() | _gn_general, stream()), 'of_gn_apply')
+    if _PROFILE is not None:
+        es = 2 if x0.dtype == torch.bfloat16 else 4
+        _PROFILE.append(dict(kind='gn', M=rows, N=c, bytes=float(2 * rows * c * es), flops=0.0))
     _trace('group_norm', out)
     return out
 

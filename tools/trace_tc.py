@@ -44,15 +44,13 @@ for d, cin, cout in shapes:
     t = buf.cpu().numpy()
     k = 7 * (cin + d - 1)
     print('== depth %d rows %d K %d N %d: %.1f us (traced launch), block %d' % (d, n, k, cout, e0.elapsed_time(e1) * 1e3, block))
-    m = t[0][t[0] > 0]; m = m[: len(m) // 5 * 5].reshape(-1, 5)
+    m = t[0][t[0] > 0]; m = m[: len(m) // 3 * 3].reshape(-1, 3)
     if len(m) > 2:
-        print('  MMA warp: %d stages, span %d clk' % (len(m), m[-1, 4] - m[0, 0]))
-        stat('stage ready (from prev commit)', m[1:, 0] - m[:-1, 4])
-        stat('issue first-half MMAs', m[:, 1] - m[:, 0])
-        stat('probe next stage', m[:, 2] - m[:, 1])
-        stat('issue second-half MMAs', m[:, 3] - m[:, 2])
-        stat('commits', m[:, 4] - m[:, 3])
-        stat('stage period', m[1:, 4] - m[:-1, 4])
+        print('  MMA warp: %d stages, span %d clk' % (len(m), m[-1, 2] - m[0, 0]))
+        stat('stage ready (from prev commit)', m[1:, 0] - m[:-1, 2])
+        stat('issue MMAs', m[:, 1] - m[:, 0])
+        stat('commits', m[:, 2] - m[:, 1])
+        stat('stage period', m[1:, 2] - m[:-1, 2])
     w = t[1][t[1] > 0]; w = w[: len(w) // 2 * 2].reshape(-1, 2)
     if len(w) > 2:
         print('  weight loader:')
