@@ -315,6 +315,12 @@ int of_dense_tap_table(int32_t mode, int32_t out_res_log2, int32_t batch, int32_
  * ------------------------------------------------------------------------------------------ */
 int of_mpu_eval(const of_octree_levels* oct, int32_t depth, const float* pos, int64_t npts, const float* reg,
                 float* fval, uint8_t* touched, void* stream);
+/* The same evaluation on the regular sampling grid of `calc_sdf` (reference utils/util_dualoctree.py:99-118 with
+ * get_mgrid :23-42; the 256^3 grid marching cubes consumes): point p of the size^3 grid of shape `batch_idx` is
+ * (p / size^2, (p / size) % size, p % size) * ((bbmax - bbmin) / size) + bbmin, generated inside the kernel (no
+ * coordinate tensor).  Points [head, head + count) are written to fval[head ..]; fval is the [size^3] array. */
+int of_mpu_eval_grid(const of_octree_levels* oct, int32_t depth, int32_t batch_idx, int32_t size, float bbmin,
+                     float bbmax, int64_t head, int64_t count, const float* reg, float* fval, void* stream);
 
 #ifdef __cplusplus
 }

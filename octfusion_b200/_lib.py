@@ -94,6 +94,7 @@ _PROTOS = {
     'of_dense_tap_table': (C.c_int, [_i32, _i32, _i32, _vp, _vp]),
     'of_octree_neigh27': (C.c_int, [C.POINTER(OctreeLevels), _i32, _vp, _vp]),
     'of_mpu_eval': (C.c_int, [C.POINTER(OctreeLevels), _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    'of_mpu_eval_grid': (C.c_int, [C.POINTER(OctreeLevels), _i32, _i32, _i32, _f32, _f32, _i64, _i64, _vp, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

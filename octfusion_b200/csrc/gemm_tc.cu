@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   const uint32_t bar_bfull = aux + 256, bar_bempty = aux + 288;
   const uint32_t bar_tfull = aux + 320, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  const uint32_t ready_ctr = aux + 368;                  // stages whose operands have landed (written by the scout warp)
+  // per ring slot: number of completed fills, published by the scout warp (A slots: 16 words, B slots: 4 words)
+  const uint32_t flag_a = aux + 384, flag_b = aux + 448;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::RING_BYTES + 352);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, TC_EPI_WARPS * 32);
     }
-    st_release_cta(ready_ctr, 0u);
+    for (int i = 0; i < 20; ++i) st_release_cta(flag_a + 4 * i, 0u);
     fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -504,27 +505,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     // =========================== MMA issuer ===========================
     // Issuing is nearly synchronous with execution (the tensor pipe accepts only a few MMAs ahead), so every cycle this
     // warp spends between two MMAs is a cycle the tensor pipe idles; an mbarrier wait costs 100-300 cycles even when the
-    // phase has long completed (profiles/tc_gather_experiments_r02.md).  The waits on the full barriers are therefore
-    // done by the scout warp, which publishes the number of stages whose operands have landed in a shared-memory
-    // counter; this warp only compares its stage index with a cached copy of the counter (one ld.acquire when the copy
-    // runs out), issues the stage's MMAs from converged code (elect.sync) and commits.
+    // phase has long completed (profiles/tc_gather_experiments_r02.md).  The full barriers are therefore watched by
+    // the scout warp, which publishes per ring slot the number of completed fills in shared memory; this warp only
+    // reads that word (ld.acquire, ~30 cycles), issues the stage's MMAs from converged code (elect.sync) and commits.
     constexpr uint32_t idesc = make_idesc(BN);
     int stage = 0, bstage = 0;
+    uint32_t round = 0, bround = 0;                          // fills of the current slot consumed so far
     int it = 0, tn = 0;
-    uint32_t nstage = 0, avail = 0;                          // stages consumed / stages known to be ready
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       mbar_wait(bar_tempty + 8 * as, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
-      for (int kb = 0; kb < p.num_kb; kb += KSUB, ++nstage) {
-        if (avail <= nstage) {
-          const long long t0 = clock64();
-          while ((avail = ld_acquire_cta(ready_ctr)) <= nstage) {
-            if (clock64() - t0 > 4000000000ll) {
-              printf("octfusion_b200 gemm_tc: MMA warp starved (block %d stage %u ready %u)\n", (int)blockIdx.x, nstage, avail);
-              __trap();
-            }
+      for (int kb = 0; kb < p.num_kb; kb += KSUB) {
+        {
+          uint32_t fa = ld_acquire_cta(flag_a + 4 * stage);
+          uint32_t fb = UNI ? 1u : ld_acquire_cta(flag_b + 4 * bstage);
+          if (fa <= round || (!UNI && fb <= bround)) {
+            const long long t0 = clock64();
+            do {
+              fa = ld_acquire_cta(flag_a + 4 * stage);
+              if (!UNI) fb = ld_acquire_cta(flag_b + 4 * bstage);
+              if (clock64() - t0 > 4000000000ll) {
+                printf("octfusion_b200 gemm_tc: MMA warp starved (block %d slot %d round %u)\n", (int)blockIdx.x, stage, round);
+                __trap();
+              }
+            } while (fa <= round || (!UNI && fb <= bround));
           }
         }
         const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES;
@@ -554,24 +560,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           trace_put(p, 0, tn, tr);
         }
         __syncwarp();
-        if (++stage == Cfg::A_STAGES) stage = 0;
-        if constexpr (!UNI) { if (++bstage == Cfg::B_STAGES) bstage = 0; }
+        if (++stage == Cfg::A_STAGES) { stage = 0; ++round; }
+        if constexpr (!UNI) { if (++bstage == Cfg::B_STAGES) { bstage = 0; ++bround; } }
       }
     }
   } else if (warp == TC_SCOUT_WARP) {
     // =========================== scout ===========================
-    // waits on the full barriers in consumption order and publishes the count of ready stages (see the MMA issuer)
-    int stage = 0, bstage = 0;
-    uint32_t phase = 0, bphase = 0, n = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < p.num_kb; kb += KSUB) {
-        if constexpr (!UNI) mbar_wait(bar_bfull + 8 * bstage, bphase);
-        mbar_wait(bar_full + 8 * stage, phase);
-        ++n;
-        if (lane == 0) st_release_cta(ready_ctr, n);
-        __syncwarp();
-        if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
-        if constexpr (!UNI) { if (++bstage == Cfg::B_STAGES) { bstage = 0; bphase ^= 1; } }
+    // One lane per ring slot (lanes 0..A_STAGES-1: gathered tiles, lanes 16..: weight tiles) polls its slot's full
+    // barrier with the non-blocking mbarrier.test_wait -- all slots in one instruction -- and publishes the number of
+    // completed fills of the slot (see the MMA issuer).  A slot cannot complete twice between two polls: the MMA warp
+    // must consume it in between.
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total_stages = (uint32_t)my_tiles * (uint32_t)((p.num_kb + KSUB - 1) / KSUB);
+    const bool is_a = lane < Cfg::A_STAGES;
+    const bool is_b = !UNI && lane >= 16 && lane < 16 + Cfg::B_STAGES;
+    const uint32_t nslots = is_a ? Cfg::A_STAGES : (Cfg::B_STAGES > 0 ? Cfg::B_STAGES : 1);
+    const uint32_t slot = is_a ? lane : lane - 16;
+    const uint32_t my_total = (is_a || is_b) ? (total_stages + nslots - 1 - slot) / nslots : 0u;
+    const uint32_t bar = is_a ? bar_full + 8 * slot : bar_bfull + 8 * slot;
+    const uint32_t flag = is_a ? flag_a + 4 * slot : flag_b + 4 * slot;
+    uint32_t done = 0, phase = 0;
+    const long long t0 = clock64();
+    while (__any_sync(0xffffffffu, done < my_total)) {
+      if (done < my_total && mbar_test_wait(bar, phase)) {
+        ++done; phase ^= 1u;
+        st_release_cta(flag, done);
+      }
+      if (clock64() - t0 > 40000000000ll) {
+        printf("octfusion_b200 gemm_tc: scout timeout (block %d lane %d done %u of %u)\n", (int)blockIdx.x, lane, done, my_total);
+        __trap();
       }
     }
   } else if (warp == TC_EPI_WARPS + 1) {

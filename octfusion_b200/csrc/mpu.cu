@@ -19,12 +19,28 @@ struct MpuCtx {
   int32_t fd, D, batch;
 };
 
-__global__ void __launch_bounds__(256) mpu_eval_kernel(MpuCtx c, const float* __restrict__ pos, int64_t npts,
+// regular sampling grid of calc_sdf (reference utils/util_dualoctree.py:99-118, get_mgrid :23-42): point p of the
+// size^3 grid = (p / size^2, (p / size) % size, p % size) * ((bbmax - bbmin) / size) + bbmin, in fp32 with separate
+// roundings like the numpy expression
+struct MpuGrid { int size; float step, bbmin; int batch_idx; int64_t head; };
+
+template <bool GRID>
+__global__ void __launch_bounds__(256) mpu_eval_kernel(MpuCtx c, const float* __restrict__ pos, MpuGrid gr, int64_t npts,
                                                        const float4* __restrict__ reg, float* __restrict__ fval,
                                                        uint8_t* __restrict__ touched) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npts) return;
-  const float4 q = reinterpret_cast<const float4*>(pos)[p];
+  float4 q;
+  if (GRID) {
+    const int64_t lin = gr.head + p;
+    const int iz = (int)(lin % gr.size), iy = (int)((lin / gr.size) % gr.size), ix = (int)(lin / ((int64_t)gr.size * gr.size));
+    q.x = __fadd_rn(__fmul_rn((float)ix, gr.step), gr.bbmin);
+    q.y = __fadd_rn(__fmul_rn((float)iy, gr.step), gr.bbmin);
+    q.z = __fadd_rn(__fmul_rn((float)iz, gr.step), gr.bbmin);
+    q.w = (float)gr.batch_idx;
+  } else {
+    q = reinterpret_cast<const float4*>(pos)[p];
+  }
   const int b = (int)q.w;
   float num = 0.0f, den = 0.0f;
   bool hit = false;
@@ -67,7 +83,21 @@ __global__ void __launch_bounds__(256) mpu_eval_kernel(MpuCtx c, const float* __
     }
   }
   fval[p] = num / (den + 1e-8f);
-  touched[p] = hit ? 1 : 0;
+  if (touched != nullptr) touched[p] = hit ? 1 : 0;
+}
+
+static int make_mpu_ctx(const of_octree_levels* oct, int32_t depth, MpuCtx& c, const char* who) {
+  OF_REQUIRE(oct->full_depth >= 1 && depth >= oct->full_depth && depth <= oct->depth && depth < 16,
+             "%s: depth %d outside [%d, %d]", who, depth, oct->full_depth, oct->depth);
+  c.fd = oct->full_depth; c.D = depth; c.batch = oct->batch;
+  int64_t off = 0;
+  for (int d = 0; d < 16; ++d) { c.children[d] = oct->children[d]; c.nnum[d] = oct->nnum[d]; c.row_off[d] = 0; }
+  for (int d = c.fd; d <= depth; ++d) {
+    OF_REQUIRE(oct->children[d] != nullptr, "%s: children[%d] missing", who, d);
+    c.row_off[d] = off;
+    off += oct->nnum[d];
+  }
+  return OF_OK;
 }
 
 }  // namespace of
@@ -76,22 +106,34 @@ extern "C" int of_mpu_eval(const of_octree_levels* oct, int32_t depth, const flo
                            const float* reg, float* fval, uint8_t* touched, void* stream) {
   using namespace of;
   OF_REQUIRE(oct && pos && reg && fval && touched && npts >= 0, "of_mpu_eval: null pointer / negative count");
-  OF_REQUIRE(oct->full_depth >= 1 && depth >= oct->full_depth && depth <= oct->depth && depth < 16,
-             "of_mpu_eval: depth %d outside [%d, %d]", depth, oct->full_depth, oct->depth);
   OF_REQUIRE(reinterpret_cast<uintptr_t>(pos) % 16 == 0 && reinterpret_cast<uintptr_t>(reg) % 16 == 0,
              "of_mpu_eval: pos / reg must be 16-byte aligned ([*, 4] fp32 rows)");
-  if (npts == 0) return OF_OK;
   MpuCtx c;
-  c.fd = oct->full_depth; c.D = depth; c.batch = oct->batch;
-  int64_t off = 0;
-  for (int d = 0; d < 16; ++d) { c.children[d] = oct->children[d]; c.nnum[d] = oct->nnum[d]; c.row_off[d] = 0; }
-  for (int d = c.fd; d <= depth; ++d) {
-    OF_REQUIRE(oct->children[d] != nullptr, "of_mpu_eval: children[%d] missing", d);
-    c.row_off[d] = off;
-    off += oct->nnum[d];
-  }
-  mpu_eval_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      c, pos, npts, reinterpret_cast<const float4*>(reg), fval, touched);
+  int rc = make_mpu_ctx(oct, depth, c, "of_mpu_eval");
+  if (rc) return rc;
+  if (npts == 0) return OF_OK;
+  mpu_eval_kernel<false><<<(unsigned)((npts + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      c, pos, MpuGrid{}, npts, reinterpret_cast<const float4*>(reg), fval, touched);
   OF_LAUNCH_CHECK("of_mpu_eval");
+  return OF_OK;
+}
+
+extern "C" int of_mpu_eval_grid(const of_octree_levels* oct, int32_t depth, int32_t batch_idx, int32_t size, float bbmin,
+                                float bbmax, int64_t head, int64_t count, const float* reg, float* fval, void* stream) {
+  using namespace of;
+  OF_REQUIRE(oct && reg && fval && size > 0 && head >= 0 && count >= 0 && head + count <= (int64_t)size * size * size,
+             "of_mpu_eval_grid: bad arguments");
+  OF_REQUIRE(reinterpret_cast<uintptr_t>(reg) % 16 == 0, "of_mpu_eval_grid: reg must be 16-byte aligned");
+  MpuCtx c;
+  int rc = make_mpu_ctx(oct, depth, c, "of_mpu_eval_grid");
+  if (rc) return rc;
+  if (count == 0) return OF_OK;
+  MpuGrid gr;
+  gr.size = size; gr.batch_idx = batch_idx; gr.head = head;
+  gr.step = (float)(((double)bbmax - (double)bbmin) / (double)size);      // python float (double) -> float32 scalar
+  gr.bbmin = bbmin;
+  mpu_eval_kernel<true><<<(unsigned)((count + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      c, nullptr, gr, count, reinterpret_cast<const float4*>(reg), fval + head, nullptr);
+  OF_LAUNCH_CHECK("of_mpu_eval_grid");
   return OF_OK;
 }

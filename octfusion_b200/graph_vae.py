@@ -293,5 +293,6 @@ class GraphVAE(nn.Module):
 
         def _neural_mpu(pos):                              # graph_vae.py:317-322: SDF at arbitrary points, finest depth
             return self.neural_mpu(pos, out[1], out[2])[self.depth_out][0]
+        _neural_mpu.mpu_args = (self.neural_mpu, out[1], out[2])      # lets mpu.calc_sdf generate the grid in-kernel
         output['neural_mpu'] = _neural_mpu
         return output

@@ -45,3 +45,51 @@ class NeuralMPU:
             del keep
             mpus[d] = (fval, hit.bool())
         return mpus
+
+
+    @torch.no_grad()
+    def eval_grid(self, reg_voxs, octree_out, batch_idx: int, size: int, bbmin: float, bbmax: float, head: int, count: int,
+                  out: torch.Tensor):
+        """finest-depth SDF at points [head, head+count) of the size^3 sampling grid of shape `batch_idx`, written into
+        out[head:head+count] (of_mpu_eval_grid: coordinates are generated inside the kernel)."""
+        d = self.depth
+        reg = reg_voxs[d].float().contiguous()
+        lv, keep = _levels(octree_out, d)
+        check(lib.of_mpu_eval_grid(C.byref(lv), d, batch_idx, size, float(bbmin), float(bbmax), head, count, ptr(reg),
+                                   ptr(out), stream()), 'of_mpu_eval_grid')
+        del keep
+        return out
+
+
+def get_mgrid(size: int, dim: int = 3, device='cuda'):
+    """reference utils/util_dualoctree.py:23-42: [size^dim, dim] float32 grid indices, first index slowest."""
+    c = torch.arange(size, dtype=torch.float32, device=device)
+    return torch.stack(torch.meshgrid(*([c] * dim), indexing='ij'), -1).reshape(size ** dim, dim)
+
+
+@torch.no_grad()
+def calc_sdf(model, batch_size: int = 1, size: int = 256, max_batch: int = 64 ** 3, bbmin: float = -1.0, bbmax: float = 1.0):
+    """Drop-in for reference utils/util_dualoctree.py:99-118: the SDF of `batch_size` shapes on a size^3 grid,
+    [B, size, size, size] fp32 on the device, evaluated in chunks of `max_batch` points.  `model` maps [P, 4] points
+    (x, y, z, batch index) to SDF values.  When it is the `neural_mpu` closure of `GraphVAE.decode_code` (it carries
+    `.mpu_args`), the grid coordinates are generated inside the evaluation kernel; any other callable gets explicit
+    point tensors exactly as in the reference."""
+    num = size ** 3
+    args = getattr(model, 'mpu_args', None)
+    dev = args[2].device if args is not None else 'cuda'
+    sdfs = torch.empty((batch_size, num), dtype=torch.float32, device=dev)
+    samples = None
+    for b in range(batch_size):
+        head = 0
+        while head < num:
+            tail = min(head + max_batch, num)
+            if args is not None:
+                mpu, reg_voxs, octree_out = args
+                mpu.eval_grid(reg_voxs, octree_out, b, size, bbmin, bbmax, head, tail - head, sdfs[b])
+            else:
+                if samples is None:
+                    samples = get_mgrid(size, 3, dev) * ((bbmax - bbmin) / size) + bbmin
+                pts = torch.cat([samples[head:tail], torch.full((tail - head, 1), float(b), device=dev)], 1)
+                sdfs[b, head:tail] = model(pts).reshape(-1)
+            head += max_batch
+    return sdfs.reshape(batch_size, size, size, size)

@@ -572,6 +572,48 @@ def _xyz_key(x, y, z, b, depth):
     return k | (b << 48)
 
 
+# ---------------------------------------------------------------------------------------
+# ocnn.nn.OctreeConv (third-party; NOT called by the reference -- SURVEY.md section 0 / Appendix B last row).
+# Restated from ocnn-pytorch 2.2.x as recalled: PARITY UNPINNED at the ocnn boundary (no source under /root/reference,
+# no reference test fixes the tap order or the weight layout).  Independent anchor used by the tests: on a full octree
+# layer it must equal torch.nn.functional.conv3d with zero padding on the [b, x, y, z] voxel grid.
+# ---------------------------------------------------------------------------------------
+def octree_neigh27(octree, depth, stride=1, nempty=False):
+    """`octree.get_neigh(depth, '333', stride, nempty)`: int64 [N', 27]; entry (dx+1)*9 + (dy+1)*3 + (dz+1) = index
+    (within `depth`) of the node at (x+dx, y+dy, z+dz), -1 where the cell is outside the volume or absent."""
+    from ocnn.octree import key2xyz, xyz2key
+    keys = octree.keys[depth].long()
+    x, y, z, b = key2xyz(keys, depth)
+    n = keys.shape[0]
+    out = torch.full((n, 27), -1, dtype=torch.long)
+    lim = 1 << depth
+    for t in range(27):
+        dx, dy, dz = t // 9 - 1, (t // 3) % 3 - 1, t % 3 - 1
+        nx, ny, nz = x + dx, y + dy, z + dz
+        ok = (nx >= 0) & (ny >= 0) & (nz >= 0) & (nx < lim) & (ny < lim) & (nz < lim)
+        k = xyz2key(nx.clamp(0, lim - 1), ny.clamp(0, lim - 1), nz.clamp(0, lim - 1), b, depth)
+        pos = torch.searchsorted(keys, k).clamp(max=n - 1)
+        hit = ok & (keys[pos] == k)
+        out[hit, t] = pos[hit]
+    if nempty:
+        child = octree.children[depth].long()
+        mapped = torch.where(out >= 0, child[out.clamp(min=0)], torch.full_like(out, -1))
+        out = mapped[child >= 0]
+    if stride == 2:
+        out = out[::8]
+    return out
+
+
+def octree_conv(data, octree, depth, weights, stride=1, nempty=False, bias=None):
+    """out = gather(data, neigh).flatten(1) @ weights.flatten(0, 1) (+ bias); weights [27, Cin, Cout]."""
+    neigh = octree_neigh27(octree, depth, stride, nempty)
+    buf = torch.zeros(neigh.shape[0], 27, data.shape[1], dtype=data.dtype)
+    valid = neigh >= 0
+    buf[valid] = data[neigh[valid]]
+    out = buf.flatten(1) @ weights.flatten(0, 1)
+    return out + bias if bias is not None else out
+
+
 class DualGraph:
     """Oracle counterpart of reference `DualOctree` + `post_processing_for_docnn`
     (dual_octree.py:19-63,400-409), exposing the duck-typed surface the U-Net reads

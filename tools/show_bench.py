@@ -7,3 +7,6 @@ if r:
 for l in d.get('roofline_per_layer', []):
     print('  M=%7d K=%5d N=%4d taps=%2d x%d: %7.1f us %7.1f TF' % (l['M'], l['K'], l['N'], l['taps'], l['launches_per_step'], l['us'], l['tflops']))
 print('clocks', d.get('clocks'))
+print('cpu_baseline', d.get('cpu_baseline'))
+print('library_baseline', d.get('library_baseline'))
+print('e2e', d.get('e2e'))
