@@ -47,7 +47,7 @@ class TapTable:
     """Neighbour table of the tap-gather GEMM (see include/octfusion_b200.h).
     tab/extra: record encoding (CUDA-core path).  tab_ord/multi_off/multi_types: ordinal encoding of the
     multi-neighbour slots for the tcgen05 path (of_graph_multi_index); n_multi = number of such slots."""
-    __slots__ = ('tab', 'extra', 'taps', 'rows', 'tab_ord', 'multi_off', 'multi_types', 'n_multi', '_type_blocks')
+    __slots__ = ('tab', 'extra', 'taps', 'rows', 'tab_ord', 'multi_off', 'multi_types', 'n_multi', '_type_blocks', '_scan')
 
     def __init__(self, tab: torch.Tensor, extra, taps: int):
         assert tab.dtype == torch.int32 and tab.is_contiguous()
@@ -55,6 +55,7 @@ class TapTable:
         self.rows = tab.numel() // taps
         self.tab_ord, self.multi_off, self.multi_types, self.n_multi = tab, None, None, 0
         self._type_blocks = {}
+        self._scan = None
 
     def type_block(self, ntype, node_type):
         """bf16 [rows, 64] node-type K block of the tcgen05 GEMM (graph constant, built once per ntype)."""
@@ -67,12 +68,23 @@ class TapTable:
 
     def index_multi(self, node_type=None):
         """build the ordinal-encoded table (once per graph)."""
+        cnt = self.multi_prepare()
+        return self.multi_finish(int(cnt.item()), node_type)
+
+    def multi_prepare(self):
+        """flag + scan of the multi-neighbour slots; returns their count as a device scalar (no synchronisation)"""
+        slots = self.tab.numel()
+        flags = torch.empty(slots, dtype=torch.int32, device=self.tab.device)
+        check(lib.of_graph_multi_flags(ptr(self.tab), slots, ptr(flags), stream()), 'of_graph_multi_flags')
+        self._scan = exclusive_scan_i32(flags)
+        return self._scan[-1:]
+
+    def multi_finish(self, n_multi: int, node_type=None):
         slots = self.tab.numel()
         dev = self.tab.device
-        flags = torch.empty(slots, dtype=torch.int32, device=dev)
-        check(lib.of_graph_multi_flags(ptr(self.tab), slots, ptr(flags), stream()), 'of_graph_multi_flags')
-        scan = exclusive_scan_i32(flags)
-        self.n_multi = int(scan[-1].item())
+        scan = self._scan
+        self._scan = None
+        self.n_multi = int(n_multi)
         if self.n_multi == 0:
             return self
         self.tab_ord = torch.empty_like(self.tab)
@@ -89,34 +101,62 @@ class StatPlan:
     of_gemm_args.stat_out): rows are cut into 32-row chunks, a chunk into segments at every change of sample id.
       chunk_seg      int32 [n_chunks + 1]  exclusive prefix sum of segments per chunk
       sample_seg_off int32 [B + 1], sample_seg_idx int32 [n_seg]: the segments of each sample, in row order
-    Built once per graph depth (sample ids from DualOctree.batch_id) or per dense resolution (rows_per_sample)."""
+    Built once per graph depth (sample ids from DualOctree.batch_id) or per dense resolution (rows_per_sample).
+    The segment count is data dependent: `pending_count()` exposes it as a device scalar so that a caller building
+    several plans (DualOctree: one per depth) can fetch all counts with ONE host synchronisation and then `finish`."""
     __slots__ = ('rows', 'batch', 'n_seg', 'chunk_seg', 'sample_seg_off', 'sample_seg_idx', 'sample_id',
-                 'rows_per_sample', 'rows_of_sample')
+                 'rows_per_sample', 'rows_of_sample', '_pending')
 
-    def __init__(self, rows: int, batch: int, *, sample_id=None, rows_per_sample=0, rows_of_sample=None, device=None):
+    def __init__(self, rows: int, batch: int, *, sample_id=None, rows_per_sample=0, rows_of_sample=None, device=None,
+                 defer=False):
         assert (sample_id is None) != (rows_per_sample == 0)
         dev = sample_id.device if sample_id is not None else torch.device(device)
         self.rows, self.batch = rows, batch
         self.sample_id, self.rows_per_sample, self.rows_of_sample = sample_id, rows_per_sample, rows_of_sample
-        r = torch.arange(rows, device=dev)
-        bid = sample_id.long() if sample_id is not None else r // rows_per_sample
+        self.n_seg, self._pending = None, None
+        if sample_id is None:
+            # dense layout: pure index arithmetic -> build on the host, no device synchronisation at all
+            r = torch.arange(rows)
+            self._build(r // rows_per_sample, r, torch.device('cpu'))
+            self.finish(int(self._pending[0]))
+            for name in ('chunk_seg', 'sample_seg_off', 'sample_seg_idx'):
+                setattr(self, name, getattr(self, name).to(dev))
+        else:
+            self._build(sample_id.long(), torch.arange(rows, device=dev), dev)
+            if not defer:
+                self.finish(int(self._pending[0].item()))
+
+    def _build(self, bid, r, dev):
+        rows, batch = self.rows, self.batch
         new = torch.ones(rows, dtype=torch.bool, device=dev)
         if rows > 1:
             new[1:] = (bid[1:] != bid[:-1]) | ((r[1:] & 31) == 0)
         seg_of_row = torch.cumsum(new.int(), 0) - 1
         n_chunks = (rows + 31) // 32
-        self.n_seg = int(seg_of_row[-1].item()) + 1 if rows > 0 else 0      # (one sync, once per layout)
+        count = (seg_of_row[-1:] + 1) if rows > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
         cs = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
         cs[:n_chunks] = seg_of_row[::32].int()
-        cs[n_chunks] = self.n_seg
+        cs[n_chunks:] = count.int()
         self.chunk_seg = cs
-        seg_sample = bid[new]
-        order = torch.sort(seg_sample, stable=True).indices
-        self.sample_seg_idx = order.int().contiguous()
-        cnt = torch.bincount(seg_sample, minlength=batch)
+        # segments of each sample in row order: stable sort of the per-row sample ids restricted to segment starts.
+        # Sized by rows (an upper bound of n_seg) so that no count is needed here: non-starts sort to the end.
+        key = torch.where(new, bid, torch.full_like(bid, batch))
+        order = torch.sort(key, stable=True).indices                      # row indices, segment starts first, by sample
+        self.sample_seg_idx = seg_of_row[order].int()                     # -> segment index of each start (prefix valid)
+        cnt = torch.bincount(key, minlength=batch + 1)[:batch]
         off = torch.zeros(batch + 1, dtype=torch.int32, device=dev)
         off[1:] = torch.cumsum(cnt, 0).int()
         self.sample_seg_off = off
+        self._pending = count
+
+    def pending_count(self):
+        return self._pending
+
+    def finish(self, n_seg: int):
+        self.n_seg = int(n_seg)
+        self.sample_seg_idx = self.sample_seg_idx[: max(self.n_seg, 1)].contiguous()
+        self._pending = None
+        return self
 
     def new_part(self, channels: int, gran: int):
         """partial buffer [n_seg, channels/gran, 2] fp32 (every slot is overwritten by its producer: no zeroing)"""

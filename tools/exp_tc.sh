@@ -1,17 +1,22 @@
 #!/bin/bash
-# round-2 experiment batch for the tcgen05 tap-gather GEMM: correctness first, then variants, then the timeline.
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-SH="6,128,128;6,256,128;6,384,128;6,128,256;5,256,256;5,128,256;5,768,256;5,512,512;4,512,512;4,256,256;6,64,128"
-echo "=== kernel tests"; timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_octree_conv.py tests/test_gpu_mpu.py -q --timeout 300 2>&1 | tail -15
-echo "=== model tests"; timeout 1200 python -m pytest tests/test_gpu_model.py -q --timeout 600 2>&1 | tail -8
-for v in "UNI=0 MT=2" "UNI=1 MT=2"; do
-  set -- $v
-  echo "=== variant $v"
-  env OCTFUSION_TC_${1%%=*}=${1##*=} OCTFUSION_TC_${2%%=*}=${2##*=} SHAPES="$SH" REPS=10 timeout 600 python tools/prof_conv.py 2>&1 | tail -12
+SH="6,128,128;6,256,128;6,128,256;5,128,256;5,768,256;4,512,512"
+echo "=== host tests (gpu)"; timeout 900 python -m pytest tests/test_gpu_kernels.py -q --timeout 300 -x 2>&1 | tail -5
+for e in "" "stats" "emb" "resid" "stats,emb" "stats,resid"; do
+  echo "=== EPI=$e"
+  EPI="$e" SHAPES="$SH" REPS=10 timeout 600 python tools/prof_conv.py 2>&1 | tail -6
 done
-echo "=== timeline UNI=0"
-timeout 600 python tools/trace_tc.py "6,128,128;4,512,512" 2>&1 | tail -60
-echo "=== bench"
-timeout 1500 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_4.json 2> gpurun_out/bench_4.err; tail -5 gpurun_out/bench_4.err
-python tools/show_bench.py gpurun_out/bench_4.json 2>&1 | tail -60
+echo "=== timeline EPI=stats,emb"
+EPI="stats,emb" timeout 600 python tools/trace_tc.py "6,128,128;5,128,256" 2>&1 | grep -E "==|epilogue|drain|wait acc|tile period|stage period|MMA warp"
+echo "=== timeline EPI none"
+timeout 600 python tools/trace_tc.py "6,128,128;5,128,256" 2>&1 | grep -E "==|epilogue|drain|wait acc|tile period|stage period|MMA warp"
+echo "=== bench fused"
+timeout 1500 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-library-baseline > gpurun_out/bench_5a.json 2> gpurun_out/bench_5a.err; tail -3 gpurun_out/bench_5a.err
+python tools/show_bench.py gpurun_out/bench_5a.json 2>&1 | head -20
+echo "=== bench unfused stats"
+OCTFUSION_GN_FUSE=0 timeout 1500 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-library-baseline > gpurun_out/bench_5b.json 2> gpurun_out/bench_5b.err; tail -3 gpurun_out/bench_5b.err
+python tools/show_bench.py gpurun_out/bench_5b.json 2>&1 | head -20
+echo "=== launch list (one step)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2500 -c 700 --csv --log-file gpurun_out/launches_5.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-library-baseline --no-roofline > /dev/null 2> gpurun_out/ncu_5.err; tail -2 gpurun_out/ncu_5.err
+python tools/launch_summary.py gpurun_out/launches_5.csv 2>&1 | head -40

@@ -19,6 +19,14 @@ for d, cin, cout in shapes:
     x = torch.randn((n, cin), device='cuda').bfloat16()
     conv = GraphConv(cin, cout, 7, 7, d - 1).cuda()
     reps = int(os.environ.get('REPS', 5))
+    if os.environ.get('EPI'):          # EPI=stats,emb,resid: the epilogue extras of a GraphResBlockEmbed conv
+        epi = {}
+        p = doc.plan[d]
+        if 'stats' in os.environ['EPI']: epi['stats'] = p.stat
+        if 'emb' in os.environ['EPI']: epi.update(row_add=torch.randn((B, cout), device='cuda'), row_add_idx=p.batch_id)
+        if 'resid' in os.environ['EPI']: epi['resid'] = torch.randn((n, cout), device='cuda').bfloat16()
+        conv_ = conv
+        conv = lambda x, doc, d: conv_.run(x, doc.plan[d], **epi)
     for _ in range(2):
         y = conv(x, doc, d)
     torch.cuda.synchronize()

@@ -32,6 +32,14 @@ for d, cin, cout in shapes:
     n = doc.plan[d].rows
     x = torch.randn((n, cin), device='cuda').bfloat16()
     conv = GraphConv(cin, cout, 7, 7, d - 1).cuda()
+    if os.environ.get('EPI'):
+        epi = {}
+        pl = doc.plan[d]
+        if 'stats' in os.environ['EPI']: epi['stats'] = pl.stat
+        if 'emb' in os.environ['EPI']: epi.update(row_add=torch.randn((B, cout), device='cuda'), row_add_idx=pl.batch_id)
+        if 'resid' in os.environ['EPI']: epi['resid'] = torch.randn((n, cout), device='cuda').bfloat16()
+        conv_ = conv
+        conv = lambda x, doc, d: conv_.run(x, doc.plan[d], **epi)
     for _ in range(2):
         conv(x, doc, d)
     torch.cuda.synchronize()
