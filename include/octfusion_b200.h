@@ -117,6 +117,8 @@ typedef struct of_gemm_args {
    * when stat_sample is NULL.  Requires N % 32 == 0 and out_rows == NULL.  NULL = off.                        */
   float* stat_out;
   const int32_t* stat_chunk_seg;
+  const int32_t* stat_seg_slot;                  /* [n_segments] row of stat_out that segment s writes: segments are
+                                                  * stored SAMPLE-MAJOR so that of_gn_finalize streams contiguous rows  */
   const int32_t* stat_sample;
   int32_t stat_rows_per_sample;
 } of_gemm_args;
@@ -151,17 +153,19 @@ int of_repack_weight(const float* src, int64_t s_tap, int64_t s_c, int64_t s_n,
  *   stats:    part [n_segments, C/gran, 2] fp32 = (sum x, sum x^2) per granule of `gran` (2 or 4) channels of each segment, one thread
  *             per (chunk, channel vector), rows added in order.  The tcgen05 GEMM writes the same buffer from its
  *             epilogue (stat_out), in which case this pass is skipped.
- *   finalize: for sample b the segments sample_seg_idx[sample_seg_off[b] .. sample_seg_off[b+1]) are summed in that
- *             order in fp64 -> mean / variance per group -> scale/shift [B, C] fp32 (gamma, beta folded in).
+ *             Slot of segment s in `part`: seg_slot[s] -- the segments of a sample occupy CONSECUTIVE slots (sample-major,
+ *             row order inside the sample).
+ *   finalize: for sample b the slots sample_seg_off[b] .. sample_seg_off[b+1] are summed in that order in fp64
+ *             (contiguous, coalesced reads) -> mean / variance per group -> scale/shift [B, C] fp32 (gamma, beta folded in).
  *             The normalised tensor is the concat (x0 | x1): part0 / part1 are the partial buffers of the two
  *             tensors with their granule widths (c1 = 0: one tensor).  C/groups and c0 must be multiples of the granules.
  *   apply:    y[r, c] = act(x[r, c] * scale[b, c] + shift[b, c])   act: 0 none, 1 SiLU, 2 GELU (erf)
  * ------------------------------------------------------------------------------------------ */
 int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
-                const int32_t* chunk_seg, const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
-                int32_t dtype, int32_t gran, float* part, void* stream);
+                const int32_t* chunk_seg, const int32_t* seg_slot, const int32_t* sample_id, int32_t rows_per_sample,
+                int64_t rows, int32_t dtype, int32_t gran, float* part, void* stream);
 int of_gn_finalize(const float* part0, int32_t c0, int32_t gran0, const float* part1, int32_t c1, int32_t gran1,
-                   const int32_t* sample_seg_off, const int32_t* sample_seg_idx,
+                   const int32_t* sample_seg_off,
                    const int32_t* rows_of_sample, int32_t rows_per_sample,
                    const float* gamma, const float* beta, int32_t batch, int32_t groups, float eps,
                    float count_eps, float* scale, float* shift, void* stream);

@@ -39,7 +39,8 @@ class GemmArgs(C.Structure):
         ('rows_a0', _i32), ('rows_a1', _i32),
         ('nt_block', _vp),
         ('reverse', _i32),
-        ('stat_out', _vp), ('stat_chunk_seg', _vp), ('stat_sample', _vp), ('stat_rows_per_sample', _i32),
+        ('stat_out', _vp), ('stat_chunk_seg', _vp), ('stat_seg_slot', _vp), ('stat_sample', _vp),
+        ('stat_rows_per_sample', _i32),
     ]
 
 
@@ -65,8 +66,8 @@ _PROTOS = {
     'of_pack_weight_tc_bytes': (_i64, [_i32, _i32, _i32, _i32]),
     'of_pack_weight_tc': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'of_repack_weight': (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
-    'of_gn_stats': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
-    'of_gn_finalize': (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _f32, _f32,
+    'of_gn_stats': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
+    'of_gn_finalize': (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _f32, _f32,
                                  _vp, _vp, _vp]),
     'of_gn_apply': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     'of_attention': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -104,7 +105,7 @@ class LibraryMissing(ImportError):
     pass
 
 
-ABI_VERSION = 2          # of_version() of the header this binding mirrors
+ABI_VERSION = 3          # of_version() of the header this binding mirrors
 
 
 def _load():

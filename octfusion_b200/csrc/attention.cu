@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// bf16 tensor-core path (ch in {32, 64, 128}): flash-style, one CTA per (shape, head, 64 queries).
+// bf16 tensor-core path (ch in {16, 32, 64, 128}): flash-style, one CTA per (shape, head, 64 queries).
 // K and V of the (shape, head) are staged once in shared memory by 16-byte cp.async (rows padded by 16 B: the
 // ldmatrix row addresses of an 8x8 tile then fall into 8 different 16-byte bank groups); each of the 4 warps owns
 // 16 query rows: S = Q K^T per 64-key block with mma.sync.m16n8k16 (bf16 x bf16 -> fp32), online softmax in fp32
@@ -119,6 +119,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -199,12 +202,18 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __nv_bfloat16* 
       sc[nt][0] = 0.f; sc[nt][1] = 0.f; sc[nt][2] = 0.f; sc[nt][3] = 0.f;
       // one ldmatrix.x4 = the (b0, b1) fragments of two 16-channel steps of this key tile
       const uint32_t a = sK + (uint32_t)(k0 + nt * 8 + (lane & 7)) * RS + ((lane >> 3) * 8) * 2;
+      if constexpr (CH == 16) {                            // one 16-channel step: ldmatrix.x2 (lanes 0-15 give the rows)
+        uint32_t b0, b1;
+        ldsm_x2(sK + (uint32_t)(k0 + nt * 8 + (lane & 7)) * RS + (((lane >> 3) & 1) * 8) * 2, b0, b1);
+        mma_bf16_16816(sc[nt], qf[0], b0, b1);
+      } else {
 #pragma unroll
-      for (int kp = 0; kp < CH / 32; ++kp) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(a + kp * 64, b0, b1, b2, b3);
-        mma_bf16_16816(sc[nt], qf[2 * kp], b0, b1);
-        mma_bf16_16816(sc[nt], qf[2 * kp + 1], b2, b3);
+        for (int kp = 0; kp < CH / 32; ++kp) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(a + kp * 64, b0, b1, b2, b3);
+          mma_bf16_16816(sc[nt], qf[2 * kp], b0, b1);
+          mma_bf16_16816(sc[nt], qf[2 * kp + 1], b2, b3);
+        }
       }
     }
     // ---- online softmax (rows g and g+8 of the warp tile; a row lives in the 4 lanes of a quad) ----
@@ -303,9 +312,10 @@ extern "C" int of_attention(const void* qkv, int64_t ld_qkv, void* out, int64_t 
     static int force_simt = -1;                            // OCTFUSION_ATT_SIMT=1: CUDA-core kernel for every shape
     if (force_simt < 0) { const char* e = getenv("OCTFUSION_ATT_SIMT"); force_simt = e ? atoi(e) : 0; }
     // tensor-core path: bf16, 16-byte aligned rows
-    if (dtype == OF_BF16 && !force_simt && (ch == 32 || ch == 64 || ch == 128) && ld_qkv % 8 == 0 && ld_out % 2 == 0 &&
+    if (dtype == OF_BF16 && !force_simt && (ch == 16 || ch == 32 || ch == 64 || ch == 128) && ld_qkv % 8 == 0 && ld_out % 2 == 0 &&
         reinterpret_cast<uintptr_t>(qkv) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0) {
-      int rc = ch == 32 ? launch_attention_tc<32>(qkv, ld_qkv, out, ld_out, batch, tokens, heads, st)
+      int rc = ch == 16 ? launch_attention_tc<16>(qkv, ld_qkv, out, ld_out, batch, tokens, heads, st)
+             : ch == 32 ? launch_attention_tc<32>(qkv, ld_qkv, out, ld_out, batch, tokens, heads, st)
              : ch == 64 ? launch_attention_tc<64>(qkv, ld_qkv, out, ld_out, batch, tokens, heads, st)
                         : launch_attention_tc<128>(qkv, ld_qkv, out, ld_out, batch, tokens, heads, st);
       if (rc == OF_OK) {

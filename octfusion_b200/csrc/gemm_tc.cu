@@ -382,12 +382,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         const __nv_bfloat16* res =
             (row_ok && g.resid) ? reinterpret_cast<const __nv_bfloat16*>(g.resid) + (int64_t)m * g.ld_resid : nullptr;
         // ---- group-norm partial statistics of this 32-row chunk (see of_gemm_args.stat_out) ----
-        int seg0 = 0, nseg = 0, my_seg = 0;
+        int seg0 = 0, nseg = 0, my_seg = 0, my_slot = 0;
         if (g.stat_out != nullptr) {
           const int chunk = (mt0 + h * TC_BM) / 32 + warp;
           if (chunk * 32 < g.M) {
             seg0 = __ldg(g.stat_chunk_seg + chunk);
             nseg = __ldg(g.stat_chunk_seg + chunk + 1) - seg0;
+            if (lane < nseg) my_slot = __ldg(g.stat_seg_slot + seg0 + lane);   // lane s: slot of the chunk's segment s
             if (nseg > 1) {                                // rows of several samples in this chunk: rank of my sample run
               const int b = row_ok ? (g.stat_sample ? __ldg(g.stat_sample + m) : m / g.stat_rows_per_sample) : -1;
               const int bp = __shfl_up_sync(0xffffffffu, b, 1);
@@ -406,12 +407,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           const bool full = (nb + CH <= g.N);
           if (row_ok) {
             if (g.bias) {
+              if (full && (reinterpret_cast<uintptr_t>(g.bias) % 16 == 0)) {
 #pragma unroll
-              for (int j = 0; j < CH; ++j) if (full || nb + j < g.N) v[j] += g.bias[nb + j];
+                for (int q = 0; q < CH / 4; ++q) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + nb) + q);
+                  v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) if (full || nb + j < g.N) v[j] += g.bias[nb + j];
+              }
             }
             if (radd) {
+              // emb[batch] row: 16-byte loads (the 32 scalar loads per chunk this replaces made the epilogue of the
+              // short-K layers 3x longer than their main loop); the rows of a warp nearly always share one sample, so
+              // these are broadcast hits
+              if (full && (g.ld_row_add % 4 == 0) && (reinterpret_cast<uintptr_t>(g.row_add) % 16 == 0)) {
 #pragma unroll
-              for (int j = 0; j < CH; ++j) if (full || nb + j < g.N) v[j] += radd[nb + j];
+                for (int q = 0; q < CH / 4; ++q) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(radd + nb) + q);
+                  v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) if (full || nb + j < g.N) v[j] += radd[nb + j];
+              }
             }
             if (res) {
               if (full && (g.ld_resid % 8 == 0)) {
@@ -464,19 +484,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
                 a[2 * q + 1] = row_ok ? qv : 0.0f;
               }
               const int nval = g.N / GRAN * 2;             // floats per segment slot
-              float* dst = g.stat_out + (int64_t)seg0 * nval + nb / GRAN * 2 + (NV == 16 ? (lane >> 1) : lane);
+              float* dst = g.stat_out + nb / GRAN * 2 + (NV == 16 ? (lane >> 1) : lane);
               const bool writer = NV == 32 || (lane & 1) == 0;
               if (nseg == 1) {
+                const int slot = __shfl_sync(0xffffffffu, my_slot, 0);
                 warp_reduce_vals<NV>(a, lane);
-                if (writer) *dst = a[0];
+                if (writer) dst[(int64_t)slot * nval] = a[0];
               } else {
 #pragma unroll 1
                 for (int s = 0; s < nseg; ++s) {
+                  const int slot = __shfl_sync(0xffffffffu, my_slot, s);
                   float t[NV];
 #pragma unroll
                   for (int j = 0; j < NV; ++j) t[j] = (my_seg == s) ? a[j] : 0.0f;
                   warp_reduce_vals<NV>(t, lane);
-                  if (writer) dst[(int64_t)s * nval] = t[0];
+                  if (writer) dst[(int64_t)slot * nval] = t[0];
                 }
               }
             }
@@ -894,9 +916,9 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
                  reinterpret_cast<uintptr_t>(a.w) % 16 == 0,
              "of_gather_gemm_tc: a0/a1/w must be 16-byte aligned");
   if (a.stat_out != nullptr) {
-    OF_REQUIRE(a.N % 32 == 0 && a.out_rows == nullptr && a.stat_chunk_seg != nullptr &&
+    OF_REQUIRE(a.N % 32 == 0 && a.out_rows == nullptr && a.stat_chunk_seg != nullptr && a.stat_seg_slot != nullptr &&
                    (a.stat_sample != nullptr || a.stat_rows_per_sample > 0),
-               "of_gather_gemm_tc: stat_out needs N %% 32 == 0, no out_rows, stat_chunk_seg and a sample map");
+               "of_gather_gemm_tc: stat_out needs N %% 32 == 0, no out_rows, stat_chunk_seg, stat_seg_slot and a sample map");
   }
   if (a.M == 0) return OF_OK;
   TcParams p;

@@ -91,7 +91,8 @@ __device__ __forceinline__ bool chunk_is_uniform(const GnSrc& s, int64_t r0, int
 // epilogue produces (of_gemm_args.stat_out), so of_gn_finalize serves both.  A new segment starts at every change
 // of sample id inside the chunk.
 template <typename T, int V, int GRAN>
-__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* __restrict__ chunk_seg, float* __restrict__ part) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* __restrict__ chunk_seg,
+                                                       const int32_t* __restrict__ seg_slot, float* __restrict__ part) {
   const int C = s.c0 + s.c1;
   const int tpr = C / V;                                   // threads per chunk
   const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* _
   auto flush = [&]() {
 #pragma unroll
     for (int i = 0; i < G; ++i) {
-      *reinterpret_cast<float2*>(part + (int64_t)seg * half + (cv / GRAN + i) * 2) = make_float2(sum[i], sq[i]);
+      *reinterpret_cast<float2*>(part + (int64_t)seg_slot[seg] * half + (cv / GRAN + i) * 2) = make_float2(sum[i], sq[i]);
       sum[i] = 0.0f; sq[i] = 0.0f;
     }
   };
@@ -140,7 +141,6 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* _
 __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ part0, int c0, int gran0,
                                                             const float* __restrict__ part1, int c1, int gran1,
                                                             const int32_t* __restrict__ seg_off,
-                                                            const int32_t* __restrict__ seg_idx,
                                                             const int32_t* __restrict__ rows_of_sample, int rows_per_sample,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int groups, float eps, float count_eps, float* __restrict__ scale,
@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
   const int j = threadIdx.x % nval, sl = threadIdx.x / nval;
   const int k0 = seg_off[b], k1 = seg_off[b + 1];
   if (sl < slices) {
-    // contiguous sub-range of the sample's segment list for this slice; four interleaved accumulators, fixed order
+    // contiguous sub-range of the sample's slots for this slice; eight independent loads in flight, four interleaved
+    // accumulators, fixed order
     const int n = k1 - k0;
     const int per = (n + slices - 1) / slices;
     const int a = k0 + sl * per, e = min(a + per, k1);
@@ -164,17 +165,14 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
     const int64_t stride = j < h0 ? h0 : h1;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     int k = a;
-    for (; k + 3 < e; k += 4) {
-      int s4[4];
+    for (; k + 7 < e; k += 8) {
+      float v8[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) s4[u] = seg_idx[k + u];
-      float v4[4];
+      for (int u = 0; u < 8; ++u) v8[u] = src[(int64_t)(k + u) * stride];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v4[u] = src[(int64_t)s4[u] * stride];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] += (double)v4[u];
+      for (int u = 0; u < 8; ++u) acc[u & 3] += (double)v8[u];
     }
-    for (int u = 0; k < e; ++k, ++u) acc[u] += (double)src[(int64_t)seg_idx[k] * stride];
+    for (int u = 0; k < e; ++k, ++u) acc[u & 3] += (double)src[(int64_t)k * stride];
     red[(size_t)sl * nval + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   }
   __syncthreads();
@@ -305,14 +303,14 @@ static int check_src(const GnSrc& s, const char* who) {
 }  // namespace of
 
 extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
-                           const int32_t* chunk_seg, const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
-                           int32_t dtype, int32_t gran, float* part, void* stream) {
+                           const int32_t* chunk_seg, const int32_t* seg_slot, const int32_t* sample_id,
+                           int32_t rows_per_sample, int64_t rows, int32_t dtype, int32_t gran, float* part, void* stream) {
   using namespace of;
   GnSrc s{x0, ld0, c0, x1, ld1, c1, sample_id, rows_per_sample, rows};
   int rc = check_src(s, "of_gn_stats");
   if (rc) return rc;
   const int C = c0 + c1;
-  OF_REQUIRE(chunk_seg != nullptr && part != nullptr, "of_gn_stats: null chunk_seg/part");
+  OF_REQUIRE(chunk_seg != nullptr && seg_slot != nullptr && part != nullptr, "of_gn_stats: null chunk_seg/seg_slot/part");
   OF_REQUIRE(dtype == OF_F32 || dtype == OF_BF16, "of_gn_stats: bad dtype");
   OF_REQUIRE(gran == 2 || gran == 4, "of_gn_stats: gran must be 2 or 4");
   const int esz = dtype == OF_F32 ? 4 : 2;
@@ -328,8 +326,8 @@ extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define OF_GN_STATS(T, VV)                                                                     \
   do {                                                                                         \
-    if (gran == 4) gn_stats_kernel<T, VV, 4><<<grid, 256, 0, st>>>(s, chunk_seg, part);        \
-    else gn_stats_kernel<T, VV, 2><<<grid, 256, 0, st>>>(s, chunk_seg, part);                  \
+    if (gran == 4) gn_stats_kernel<T, VV, 4><<<grid, 256, 0, st>>>(s, chunk_seg, seg_slot, part);        \
+    else gn_stats_kernel<T, VV, 2><<<grid, 256, 0, st>>>(s, chunk_seg, seg_slot, part);                  \
   } while (0)
   if (dtype == OF_F32) OF_GN_STATS(float, 4);
   else if (V == 8) OF_GN_STATS(__nv_bfloat16, 8);
@@ -340,12 +338,12 @@ extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* 
 }
 
 extern "C" int of_gn_finalize(const float* part0, int32_t c0, int32_t gran0, const float* part1, int32_t c1,
-                              int32_t gran1, const int32_t* sample_seg_off, const int32_t* sample_seg_idx,
+                              int32_t gran1, const int32_t* sample_seg_off,
                               const int32_t* rows_of_sample, int32_t rows_per_sample, const float* gamma,
                               const float* beta, int32_t batch, int32_t groups, float eps, float count_eps,
                               float* scale, float* shift, void* stream) {
   using namespace of;
-  OF_REQUIRE(part0 && gamma && beta && scale && shift && sample_seg_off && sample_seg_idx, "of_gn_finalize: null pointer");
+  OF_REQUIRE(part0 && gamma && beta && scale && shift && sample_seg_off, "of_gn_finalize: null pointer");
   OF_REQUIRE((part1 == nullptr) == (c1 == 0), "of_gn_finalize: part1/c1 inconsistent");
   OF_REQUIRE((gran0 == 2 || gran0 == 4) && (c1 == 0 || gran1 == 2 || gran1 == 4), "of_gn_finalize: granules must be 2 or 4");
   if (c1 == 0) gran1 = gran0;
@@ -363,7 +361,7 @@ extern "C" int of_gn_finalize(const float* part0, int32_t c0, int32_t gran0, con
   const int threads = slices * nval;
   const size_t smem = ((size_t)slices * nval + nval) * sizeof(double);
   gn_finalize_kernel<<<batch, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      part0, c0, gran0, part1, c1, gran1, sample_seg_off, sample_seg_idx, rows_of_sample, rows_per_sample, gamma, beta,
+      part0, c0, gran0, part1, c1, gran1, sample_seg_off, rows_of_sample, rows_per_sample, gamma, beta,
       groups, eps, count_eps, scale, shift);
   OF_LAUNCH_CHECK("of_gn_finalize");
   return OF_OK;

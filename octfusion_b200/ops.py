@@ -101,10 +101,12 @@ class StatPlan:
     of_gemm_args.stat_out): rows are cut into 32-row chunks, a chunk into segments at every change of sample id.
       chunk_seg      int32 [n_chunks + 1]  exclusive prefix sum of segments per chunk
       sample_seg_off int32 [B + 1], sample_seg_idx int32 [n_seg]: the segments of each sample, in row order
+      seg_slot       int32 [n_seg]  row of the partial buffers that segment s owns = its rank in sample_seg_idx, so a
+                     sample's partials are contiguous rows [sample_seg_off[b], sample_seg_off[b+1])
     Built once per graph depth (sample ids from DualOctree.batch_id) or per dense resolution (rows_per_sample).
     The segment count is data dependent: `pending_count()` exposes it as a device scalar so that a caller building
     several plans (DualOctree: one per depth) can fetch all counts with ONE host synchronisation and then `finish`."""
-    __slots__ = ('rows', 'batch', 'n_seg', 'chunk_seg', 'sample_seg_off', 'sample_seg_idx', 'sample_id',
+    __slots__ = ('rows', 'batch', 'n_seg', 'chunk_seg', 'sample_seg_off', 'sample_seg_idx', 'seg_slot', 'sample_id',
                  'rows_per_sample', 'rows_of_sample', '_pending')
 
     def __init__(self, rows: int, batch: int, *, sample_id=None, rows_per_sample=0, rows_of_sample=None, device=None,
@@ -119,7 +121,7 @@ class StatPlan:
             r = torch.arange(rows)
             self._build(r // rows_per_sample, r, torch.device('cpu'))
             self.finish(int(self._pending[0]))
-            for name in ('chunk_seg', 'sample_seg_off', 'sample_seg_idx'):
+            for name in ('chunk_seg', 'sample_seg_off', 'sample_seg_idx', 'seg_slot'):
                 setattr(self, name, getattr(self, name).to(dev))
         else:
             self._build(sample_id.long(), torch.arange(rows, device=dev), dev)
@@ -155,6 +157,10 @@ class StatPlan:
     def finish(self, n_seg: int):
         self.n_seg = int(n_seg)
         self.sample_seg_idx = self.sample_seg_idx[: max(self.n_seg, 1)].contiguous()
+        self.seg_slot = torch.zeros(max(self.n_seg, 1), dtype=torch.int32, device=self.sample_seg_idx.device)
+        if self.n_seg > 0:
+            self.seg_slot[self.sample_seg_idx.long()] = torch.arange(self.n_seg, dtype=torch.int32,
+                                                                     device=self.sample_seg_idx.device)
         self._pending = None
         return self
 
@@ -305,11 +311,12 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g.M, g.N = m, n
     g.dtype = dt(a0)
     st_obj = None
-    g.stat_out, g.stat_chunk_seg, g.stat_sample, g.stat_rows_per_sample = None, None, None, 0
+    g.stat_out, g.stat_chunk_seg, g.stat_seg_slot, g.stat_sample, g.stat_rows_per_sample = None, None, None, None, 0
     if (stats is not None and _FUSE_STATS and use_tc and n % 32 == 0 and out_rows is None and stats.rows == m
             and not g.out_f32):
         st_obj = Stats(stats.new_part(n, tc_stat_gran(n)), stats, n, tc_stat_gran(n))
         g.stat_out, g.stat_chunk_seg = st_obj.part.data_ptr(), stats.chunk_seg.data_ptr()
+        g.stat_seg_slot = stats.seg_slot.data_ptr()
         g.stat_sample = stats.sample_id.data_ptr() if stats.sample_id is not None else None
         g.stat_rows_per_sample = stats.rows_per_sample
     prof = _PROFILE
@@ -376,7 +383,7 @@ def _stats_of(x, plan: StatPlan, cpg: int):
         return st.part, st.gran
     gran = 4 if cpg % 4 == 0 else 2
     part = plan.new_part(x.shape[1], gran)
-    check(lib.of_gn_stats(ptr(x), x.stride(0), x.shape[1], None, 0, 0, ptr(plan.chunk_seg), ptr(plan.sample_id),
+    check(lib.of_gn_stats(ptr(x), x.stride(0), x.shape[1], None, 0, 0, ptr(plan.chunk_seg), ptr(plan.seg_slot), ptr(plan.sample_id),
                           plan.rows_per_sample, x.shape[0], dt(x), gran, ptr(part), stream()), 'of_gn_stats')
     return part, gran
 
@@ -401,7 +408,7 @@ def group_norm(x0, gamma, beta, groups: int, plan: StatPlan, *, x1=None, eps=1e-
     p1, g1 = _stats_of(x1, plan, cpg) if x1 is not None else (None, g0)
     scale = torch.empty((batch, c), dtype=torch.float32, device=dev)
     shift = torch.empty((batch, c), dtype=torch.float32, device=dev)
-    check(lib.of_gn_finalize(ptr(p0), c0, g0, ptr(p1), c1, g1, ptr(plan.sample_seg_off), ptr(plan.sample_seg_idx),
+    check(lib.of_gn_finalize(ptr(p0), c0, g0, ptr(p1), c1, g1, ptr(plan.sample_seg_off),
                              ptr(plan.rows_of_sample), plan.rows_per_sample, ptr(gamma), ptr(beta), batch, groups,
                              float(eps), float(count_eps), ptr(scale), ptr(shift), stream()), 'of_gn_finalize')
     if out is None:

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), 'library does not export %s' % name
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.of_version() == 2
+    assert lib.of_version() == 3
 
 
 def test_argument_validation_without_gpu():
@@ -214,6 +214,8 @@ def test_stat_plan_segment_tables():
         for b in range(batch):
             mine = idx[off[b]:off[b + 1]]
             assert mine == [k for k, s in enumerate(ss) if s == b]          # in row order
+        slot = sp.seg_slot.tolist()
+        assert sorted(slot) == list(range(len(ss))) and all(slot[s] == k for k, s in enumerate(idx))
     for rows_per_sample, batch in ((8, 5), (64, 3), (4096, 2)):
         sp = StatPlan(rows_per_sample * batch, batch, rows_per_sample=rows_per_sample, device='cpu')
         cs, ss = brute([r // rows_per_sample for r in range(rows_per_sample * batch)])
