@@ -267,7 +267,7 @@ struct TcCfg {
   static constexpr int A_STAGES = (BUDGET - B_STAGES * B_BYTES) / STAGE_BYTES;
   static constexpr int ACC_COLS = 2 * MT * BN;                      // two accumulator sets (MMA of tile i+1 || epilogue of tile i)
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int AUX_BYTES = 512;                             // mbarriers + tmem slot
+  static constexpr int AUX_BYTES = 512 + TC_EPI_WARPS * 1024;       // mbarriers + tmem slot | per-epilogue-warp row of (bias + emb)
   static constexpr int RING_BYTES = A_STAGES * STAGE_BYTES + B_STAGES * B_BYTES;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + AUX_BYTES;
   static_assert(A_STAGES >= 2 && A_STAGES <= 16, "ring depth");
@@ -381,6 +381,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         const float* radd = (row_ok && g.row_add) ? g.row_add + (int64_t)g.row_add_idx[m] * g.ld_row_add : nullptr;
         const __nv_bfloat16* res =
             (row_ok && g.resid) ? reinterpret_cast<const __nv_bfloat16*>(g.resid) + (int64_t)m * g.ld_resid : nullptr;
+        // ---- per-column addends (bias + emb[batch]): when the 32 rows of this warp share one sample -- nearly always --
+        // the BN-wide row is staged ONCE per row tile in the warp's shared-memory slot and read back as broadcast
+        // ld.shared.v4 per chunk; per-row global loads (L2 latency on every chunk: the 13 KB of L1 left beside the rings
+        // do not hold them) made the epilogue of the short-K layers longer than their main loop
+        bool staged = false;
+        const uint32_t my_stage = aux + 512 + warp * 1024;
+        if ((g.bias != nullptr || g.row_add != nullptr) && n0 + BN <= g.N && (g.N % 4 == 0) &&
+            (g.row_add == nullptr || (g.ld_row_add % 4 == 0 && reinterpret_cast<uintptr_t>(g.row_add) % 16 == 0)) &&
+            (g.bias == nullptr || reinterpret_cast<uintptr_t>(g.bias) % 16 == 0)) {
+          const int bsel = (row_ok && g.row_add) ? g.row_add_idx[m] : -1;
+          const int b0 = __shfl_sync(0xffffffffu, bsel, 0);
+          if (__all_sync(0xffffffffu, !row_ok || bsel == b0) && (g.row_add == nullptr || b0 >= 0)) {
+            staged = true;
+            __syncwarp();                                   // the previous row tile's reads of the slot are done
+#pragma unroll
+            for (int i = lane * 4; i < BN; i += 128) {
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (g.bias) t = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + i));
+              if (g.row_add) {
+                const float4 e = __ldg(reinterpret_cast<const float4*>(g.row_add + (int64_t)b0 * g.ld_row_add + n0 + i));
+                t.x += e.x; t.y += e.y; t.z += e.z; t.w += e.w;
+              }
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(my_stage + i * 4), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+            }
+            __syncwarp();
+          }
+        }
         // ---- group-norm partial statistics of this 32-row chunk (see of_gemm_args.stat_out) ----
         int seg0 = 0, nseg = 0, my_seg = 0, my_slot = 0;
         if (g.stat_out != nullptr) {
@@ -405,8 +432,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 #pragma unroll
           for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(acc[j]);
           const bool full = (nb + CH <= g.N);
+          if (staged) {
+#pragma unroll
+            for (int q = 0; q < CH / 4; ++q) {
+              float4 t;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(my_stage + (c0 + 4 * q) * 4));
+              v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+            }
+          }
           if (row_ok) {
-            if (g.bias) {
+            if (g.bias && !staged) {
               if (full && (reinterpret_cast<uintptr_t>(g.bias) % 16 == 0)) {
 #pragma unroll
                 for (int q = 0; q < CH / 4; ++q) {
@@ -418,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
                 for (int j = 0; j < CH; ++j) if (full || nb + j < g.N) v[j] += g.bias[nb + j];
               }
             }
-            if (radd) {
+            if (radd && !staged) {
               // emb[batch] row: 16-byte loads (the 32 scalar loads per chunk this replaces made the epilogue of the
               // short-K layers 3x longer than their main loop); the rows of a warp nearly always share one sample, so
               // these are broadcast hits

@@ -1,5 +1,5 @@
-"""Times of_gn_stats / of_gn_apply alone at the full B=32 size: achieved GB/s against the HBM peak.
-usage: python tools/prof_gn.py ; env REPS"""
+"""Times of_gn_stats / of_gn_finalize / of_gn_apply alone at the full B=32 size: achieved GB/s against the HBM peak.
+usage: python tools/prof_gn.py ; env REPS, OCTFUSION_GN_CHUNK_KB"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -31,15 +31,19 @@ for d, c0, c1 in ((6, 128, 0), (6, 128, 128), (5, 256, 0), (5, 256, 256), (4, 51
     x0 = torch.randn((n, c0), device='cuda').bfloat16()
     x1 = torch.randn((n, c1), device='cuda').bfloat16() if c1 else None
     c = c0 + c1
-    sums = torch.zeros((B, 32, 2), dtype=torch.float64, device='cuda')
     scale = torch.ones((B, c), device='cuda'); shift = torch.zeros((B, c), device='cuda')
+    gam = torch.ones((1, c), device='cuda'); bet = torch.zeros((1, c), device='cuda')
     out = torch.empty((n, c), dtype=torch.bfloat16, device='cuda')
     a1 = (ptr(x1), x1.stride(0), c1) if x1 is not None else (None, 0, 0)
-    st = lambda: check(lib.of_gn_stats(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], ptr(p.batch_id), 0, n, B, 32,  # noqa: E731
-                                       dt(x0), ptr(sums), 0, stream()))
+    sp = p.stat
+    part = sp.new_part(c, 4)
+    st = lambda: check(lib.of_gn_stats(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], ptr(sp.chunk_seg), ptr(sp.seg_slot),  # noqa: E731
+                                       ptr(p.batch_id), 0, n, dt(x0), 4, ptr(part), stream()))
+    fi = lambda: check(lib.of_gn_finalize(ptr(part), c, 4, None, 0, 4, ptr(sp.sample_seg_off), ptr(p.rows_of_sample), 0,  # noqa: E731
+                                          ptr(gam), ptr(bet), B, 32, 1e-5, 1e-5, ptr(scale), ptr(shift), stream()))
     ap = lambda: check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], ptr(p.batch_id), 0, n, ptr(scale),  # noqa: E731
                                        ptr(shift), 1, dt(x0), ptr(out), out.stride(0), 0, stream()))
-    ts, ta = timed(st), timed(ap)
+    ts, tf, ta = timed(st), timed(fi), timed(ap)
     byt = n * c * 2
-    print('depth %d rows %7d C %3d+%3d: stats %7.1f us %6.0f GB/s | apply %7.1f us %6.0f GB/s' %
-          (d, n, c0, c1, ts, byt / ts / 1e3, ta, 2 * byt / ta / 1e3))
+    print('depth %d rows %7d C %3d+%3d: stats %7.1f us %6.0f GB/s | finalize %6.1f us | apply %7.1f us %6.0f GB/s' %
+          (d, n, c0, c1, ts, byt / ts / 1e3, tf, ta, 2 * byt / ta / 1e3))
