@@ -47,6 +47,11 @@ int of_abi_sizeof_octree_levels(void);
 /* diagnostics: per-role clock64 stamps of CTA `block` of the following of_gather_gemm_tc launches are written to
  * buf [7][cap_per_region] (uint64); buf = NULL switches tracing off (tools/trace_tc.py decodes the stamps) */
 int of_tc_trace_set(void* buf, int32_t cap_per_region, int32_t block);
+/* kernel-variant switches of of_gather_gemm_tc (experiments / tests; a value outside the set keeps the current one):
+ * mt in {1, 2}: 128-row tiles per CTA for N <= 128; uni in {0, 1}: weight tile inside the gather ring's stage;
+ * cg in {1, 2}: 2 = CTA pairs (tcgen05 cta_group::2) for the 256-wide tiles.  Defaults: environment
+ * OCTFUSION_TC_MT / _UNI / _CG, else 2 / 0 / 1. */
+int of_tc_config(int32_t mt, int32_t uni, int32_t cg);
 
 /* ------------------------------------------------------------------------------------------
  * Tap-gather GEMM:   out[m, :] = sum_tap  mean_{j in nbr(m, tap)} [ A[j, :] | onehot(type_j) ] . W[tap]
@@ -164,11 +169,13 @@ int of_repack_weight(const float* src, int64_t s_tap, int64_t s_c, int64_t s_n,
 int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                 const int32_t* chunk_seg, const int32_t* seg_slot, const int32_t* sample_id, int32_t rows_per_sample,
                 int64_t rows, int32_t dtype, int32_t gran, float* part, void* stream);
+#define OF_GN_FINALIZE_SPLIT 8   /* CTAs per sample; scratch: batch * OF_GN_FINALIZE_SPLIT * C doubles; ticket: batch
+                                  * int32, zero on first use (the kernel leaves them zero); both may be NULL (one CTA) */
 int of_gn_finalize(const float* part0, int32_t c0, int32_t gran0, const float* part1, int32_t c1, int32_t gran1,
-                   const int32_t* sample_seg_off,
+                   const int32_t* sample_seg_off, int32_t n_segments,
                    const int32_t* rows_of_sample, int32_t rows_per_sample,
                    const float* gamma, const float* beta, int32_t batch, int32_t groups, float eps,
-                   float count_eps, float* scale, float* shift, void* stream);
+                   float count_eps, float* scale, float* shift, double* scratch, int32_t* ticket, void* stream);
 int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* x1, int64_t ld1, int32_t c1,
                 const int32_t* sample_id, int32_t rows_per_sample, int64_t rows,
                 const float* scale, const float* shift, int32_t act, int32_t dtype,

@@ -61,14 +61,15 @@ _PROTOS = {
     'of_abi_sizeof_gemm_args': (C.c_int, []),
     'of_abi_sizeof_octree_levels': (C.c_int, []),
     'of_tc_trace_set': (C.c_int, [_vp, _i32, _i32]),
+    'of_tc_config': (C.c_int, [_i32, _i32, _i32]),
     'of_gather_gemm_simt': (C.c_int, [C.POINTER(GemmArgs), _vp]),
     'of_gather_gemm_tc': (C.c_int, [C.POINTER(GemmArgs), _vp]),
     'of_pack_weight_tc_bytes': (_i64, [_i32, _i32, _i32, _i32]),
     'of_pack_weight_tc': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'of_repack_weight': (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
     'of_gn_stats': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
-    'of_gn_finalize': (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _f32, _f32,
-                                 _vp, _vp, _vp]),
+    'of_gn_finalize': (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _f32, _f32,
+                                 _vp, _vp, _vp, _vp, _vp]),
     'of_gn_apply': (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     'of_attention': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     'of_linear_small': (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
@@ -105,7 +106,7 @@ class LibraryMissing(ImportError):
     pass
 
 
-ABI_VERSION = 3          # of_version() of the header this binding mirrors
+ABI_VERSION = 4          # of_version() of the header this binding mirrors
 
 
 def _load():

@@ -135,8 +135,11 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, const int32_t* _
   flush();
 }
 
-// One CTA per sample: partial slots of the sample's segments are summed in list order (fixed order, fp64), then the
-// group statistics and the [C] scale / shift rows of the sample are formed.
+// Partial slots of a sample are summed in slot order (fixed order, fp64), then the group statistics and the [C] scale /
+// shift rows of the sample are formed.  grid = (batch, S): the S CTAs of a sample each reduce a contiguous range of
+// its slots into a fp64 scratch row; the CTA that finishes last (a ticket per sample, self-resetting) adds the S rows in
+// index order -- the ticket only decides WHO does the last step, never the order of the additions, so the result is
+// bit-reproducible -- and writes scale / shift.
 //   smem: double red[slices][nval] | double tot[nval]
 __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ part0, int c0, int gran0,
                                                             const float* __restrict__ part1, int c1, int gran1,
@@ -144,9 +147,11 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
                                                             const int32_t* __restrict__ rows_of_sample, int rows_per_sample,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int groups, float eps, float count_eps, float* __restrict__ scale,
-                                                            float* __restrict__ shift) {
+                                                            float* __restrict__ shift, double* __restrict__ scratch,
+                                                            int* __restrict__ ticket) {
   extern __shared__ double gn_sm[];
-  const int b = blockIdx.x;
+  __shared__ int is_last;
+  const int b = blockIdx.x, sb = blockIdx.y, S = gridDim.y;
   const int C = c0 + c1;
   const int h0 = c0 / gran0 * 2, h1 = c1 > 0 ? c1 / gran1 * 2 : 0;   // floats per segment slot of the two buffers
   const int nval = h0 + h1;
@@ -155,12 +160,14 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
   double* tot = gn_sm + (size_t)slices * nval;
   const int j = threadIdx.x % nval, sl = threadIdx.x / nval;
   const int k0 = seg_off[b], k1 = seg_off[b + 1];
+  const int per_blk = (k1 - k0 + S - 1) / S;
+  const int a0 = k0 + sb * per_blk, e0 = min(a0 + per_blk, k1);
   if (sl < slices) {
-    // contiguous sub-range of the sample's slots for this slice; eight independent loads in flight, four interleaved
+    // contiguous sub-range of this CTA's slots for this slice; eight independent loads in flight, four interleaved
     // accumulators, fixed order
-    const int n = k1 - k0;
+    const int n = max(e0 - a0, 0);
     const int per = (n + slices - 1) / slices;
-    const int a = k0 + sl * per, e = min(a + per, k1);
+    const int a = a0 + sl * per, e = min(a + per, e0);
     const float* src = j < h0 ? part0 + j : part1 + (j - h0);
     const int64_t stride = j < h0 ? h0 : h1;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -180,6 +187,21 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
     double t = 0.0;
     for (int q = 0; q < slices; ++q) t += red[(size_t)q * nval + threadIdx.x];
     tot[threadIdx.x] = t;
+    if (S > 1) scratch[((size_t)b * S + sb) * nval + threadIdx.x] = t;
+  }
+  if (S > 1) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&ticket[b], 1) == S - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if ((int)threadIdx.x < nval) {
+      double t = 0.0;
+      for (int q = 0; q < S; ++q) t += __ldcg(&scratch[((size_t)b * S + q) * nval + threadIdx.x]);
+      tot[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) ticket[b] = 0;                   // ready for the next launch
   }
   __syncthreads();
   const int cpg = C / groups;
@@ -188,11 +210,11 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     const int lo = g * cpg, hi = lo + cpg;                 // the group's channels: granules of x0 then of x1
-    double S = 0.0, Q = 0.0;
-    for (int ch = lo; ch < min(hi, c0); ch += gran0) { S += tot[ch / gran0 * 2]; Q += tot[ch / gran0 * 2 + 1]; }
-    for (int ch = max(lo, c0); ch < hi; ch += gran1) { S += tot[h0 + (ch - c0) / gran1 * 2]; Q += tot[h0 + (ch - c0) / gran1 * 2 + 1]; }
-    const double m = S * inv;                              // modules.py:304
-    double var = (Q - 2.0 * m * S + n * m * m) * inv;      // sum (x-m)^2 * inv_count, modules.py:308
+    double S_ = 0.0, Q = 0.0;
+    for (int ch = lo; ch < min(hi, c0); ch += gran0) { S_ += tot[ch / gran0 * 2]; Q += tot[ch / gran0 * 2 + 1]; }
+    for (int ch = max(lo, c0); ch < hi; ch += gran1) { S_ += tot[h0 + (ch - c0) / gran1 * 2]; Q += tot[h0 + (ch - c0) / gran1 * 2 + 1]; }
+    const double m = S_ * inv;                             // modules.py:304
+    double var = (Q - 2.0 * m * S_ + n * m * m) * inv;     // sum (x-m)^2 * inv_count, modules.py:308
     if (var < 0.0) var = 0.0;
     const double rstd = 1.0 / sqrt(var + (double)eps);     // modules.py:310
     const double ga = gamma[c];
@@ -338,10 +360,10 @@ extern "C" int of_gn_stats(const void* x0, int64_t ld0, int32_t c0, const void* 
 }
 
 extern "C" int of_gn_finalize(const float* part0, int32_t c0, int32_t gran0, const float* part1, int32_t c1,
-                              int32_t gran1, const int32_t* sample_seg_off,
+                              int32_t gran1, const int32_t* sample_seg_off, int32_t n_segments,
                               const int32_t* rows_of_sample, int32_t rows_per_sample, const float* gamma,
                               const float* beta, int32_t batch, int32_t groups, float eps, float count_eps,
-                              float* scale, float* shift, void* stream) {
+                              float* scale, float* shift, double* scratch, int32_t* ticket, void* stream) {
   using namespace of;
   OF_REQUIRE(part0 && gamma && beta && scale && shift && sample_seg_off, "of_gn_finalize: null pointer");
   OF_REQUIRE((part1 == nullptr) == (c1 == 0), "of_gn_finalize: part1/c1 inconsistent");
@@ -354,15 +376,19 @@ extern "C" int of_gn_finalize(const float* part0, int32_t c0, int32_t gran0, con
              "of_gn_finalize: C=%d groups=%d c0=%d: channels per group and c0 must be multiples of the granules (%d, %d)",
              C, groups, c0, gran0, gran1);
   OF_REQUIRE(rows_of_sample != nullptr || rows_per_sample > 0, "of_gn_finalize: need a row count");
-  OF_REQUIRE(batch > 0, "of_gn_finalize: bad batch");
+  OF_REQUIRE(batch > 0 && n_segments >= 0, "of_gn_finalize: bad batch / n_segments");
   const int nval = c0 / gran0 * 2 + (c1 > 0 ? c1 / gran1 * 2 : 0);
   OF_REQUIRE(nval <= 1024, "of_gn_finalize: C=%d too wide", C);
   const int slices = 1024 / nval;
   const int threads = slices * nval;
+  // CTAs per sample: ~128 slots each, at most OF_GN_FINALIZE_SPLIT; more than one needs the scratch rows and tickets
+  int S = (n_segments / batch + 127) / 128;
+  S = S < 1 ? 1 : (S > OF_GN_FINALIZE_SPLIT ? OF_GN_FINALIZE_SPLIT : S);
+  if (scratch == nullptr || ticket == nullptr) S = 1;
   const size_t smem = ((size_t)slices * nval + nval) * sizeof(double);
-  gn_finalize_kernel<<<batch, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      part0, c0, gran0, part1, c1, gran1, sample_seg_off, rows_of_sample, rows_per_sample, gamma, beta,
-      groups, eps, count_eps, scale, shift);
+  gn_finalize_kernel<<<dim3(batch, S), threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      part0, c0, gran0, part1, c1, gran1, sample_seg_off, rows_of_sample, rows_per_sample, gamma, beta, groups, eps,
+      count_eps, scale, shift, scratch, ticket);
   OF_LAUNCH_CHECK("of_gn_finalize");
   return OF_OK;
 }

@@ -375,6 +375,19 @@ _gn_general = 2 if os.environ.get('OCTFUSION_GN_GENERAL') == '1' else 0      # d
 _ACT = {False: 0, None: 0, True: 1, 'silu': 1, 'gelu': 2}
 
 
+GN_FINALIZE_SPLIT = 8          # OF_GN_FINALIZE_SPLIT of include/octfusion_b200.h
+_TICKETS = {}
+
+
+def _gn_ticket(dev, batch):
+    """per-device ticket counters of of_gn_finalize (zero-initialised once; the kernel leaves them zero)"""
+    t = _TICKETS.get(dev)
+    if t is None or t.numel() < batch:
+        t = torch.zeros(max(batch, 64), dtype=torch.int32, device=dev)
+        _TICKETS[dev] = t
+    return t
+
+
 def _stats_of(x, plan: StatPlan, cpg: int):
     """(partials, granule) of x under `plan`: those its producing GEMM attached when their granule divides the
     channels-per-group `cpg`, else one stand-alone statistics pass"""
@@ -408,9 +421,11 @@ def group_norm(x0, gamma, beta, groups: int, plan: StatPlan, *, x1=None, eps=1e-
     p1, g1 = _stats_of(x1, plan, cpg) if x1 is not None else (None, g0)
     scale = torch.empty((batch, c), dtype=torch.float32, device=dev)
     shift = torch.empty((batch, c), dtype=torch.float32, device=dev)
-    check(lib.of_gn_finalize(ptr(p0), c0, g0, ptr(p1), c1, g1, ptr(plan.sample_seg_off),
+    scratch = torch.empty(batch * GN_FINALIZE_SPLIT * c, dtype=torch.float64, device=dev)
+    check(lib.of_gn_finalize(ptr(p0), c0, g0, ptr(p1), c1, g1, ptr(plan.sample_seg_off), plan.n_seg,
                              ptr(plan.rows_of_sample), plan.rows_per_sample, ptr(gamma), ptr(beta), batch, groups,
-                             float(eps), float(count_eps), ptr(scale), ptr(shift), stream()), 'of_gn_finalize')
+                             float(eps), float(count_eps), ptr(scale), ptr(shift), ptr(scratch), ptr(_gn_ticket(dev, batch)),
+                             stream()), 'of_gn_finalize')
     if out is None:
         out = torch.empty((rows, c), dtype=x0.dtype, device=dev)
     a1 = (ptr(x1), x1.stride(0), c1) if x1 is not None else (None, 0, 0)

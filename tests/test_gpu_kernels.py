@@ -104,6 +104,44 @@ def test_graphconv_bf16_simt_equals_tc():
     assert relerr(y_tc, y_si) < 8e-3
 
 
+@pytest.fixture
+def pair_variant():
+    """run the tcgen05 GEMM's 256-wide tiles as CTA pairs (tcgen05.mma.cta_group::2) for the duration of a test"""
+    from octfusion_b200._lib import lib
+    lib.of_tc_config(-1, -1, 2)
+    yield
+    lib.of_tc_config(-1, -1, 1)
+
+
+@pytest.mark.parametrize('d,cin,cout,nt', [(4, 256, 512, 3), (5, 128, 256, 4), (6, 128, 256, 5), (5, 768, 256, 4)])
+def test_graphconv_bf16_cta_pair(pair_variant, d, cin, cout, nt):
+    """cta_group::2: two CTAs compute one 256-row tile, each gathering its 128 rows and streaming half of the weight
+    tile; same result as the oracle (and the row count of these graphs is not a multiple of 256: the last pair tile
+    has a masked half)."""
+    y, ref32, refbf = _graphconv_case(2, d, cin, cout, nt, torch.bfloat16)
+    assert relerr(y, refbf) < 8e-3
+    assert relerr(y, ref32) < 2e-2
+
+
+def test_cta_pair_equals_single_cta_bitwise(pair_variant):
+    """same MMA order per output element (K blocks in order, fp32 accumulation in TMEM): the pair variant reproduces
+    the single-CTA result bit for bit, epilogue extras and norm statistics included"""
+    from octfusion_b200._lib import lib
+    from octfusion_b200.modules import GraphConv
+    doc = product_doctree(3, 5)
+    d, cin, cout = 5, 256, 256
+    plan = doc.plan[d]
+    conv = GraphConv(cin, cout, 7, 7, d - 1).to(DEV)
+    x = _rand((plan.rows, cin), 3).to(DEV).bfloat16()
+    res = _rand((plan.rows, cout), 4).to(DEV).bfloat16()
+    emb = _rand((3, cout), 5).to(DEV)
+    run = lambda: conv.run(x, plan, row_add=emb, row_add_idx=plan.batch_id, resid=res, stats=plan.stat)  # noqa: E731
+    a = run()
+    lib.of_tc_config(-1, -1, 1)
+    b = run()
+    assert torch.equal(a, b) and torch.equal(a._of_stats.part, b._of_stats.part)
+
+
 # ------------------------------------------------------------------------------------------------
 # plain GEMMs with the fused epilogues
 # ------------------------------------------------------------------------------------------------

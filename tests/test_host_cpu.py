@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), 'library does not export %s' % name
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.of_version() == 3
+    assert lib.of_version() == 4
 
 
 def test_argument_validation_without_gpu():

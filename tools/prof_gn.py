@@ -39,8 +39,11 @@ for d, c0, c1 in ((6, 128, 0), (6, 128, 128), (5, 256, 0), (5, 256, 256), (4, 51
     part = sp.new_part(c, 4)
     st = lambda: check(lib.of_gn_stats(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], ptr(sp.chunk_seg), ptr(sp.seg_slot),  # noqa: E731
                                        ptr(p.batch_id), 0, n, dt(x0), 4, ptr(part), stream()))
-    fi = lambda: check(lib.of_gn_finalize(ptr(part), c, 4, None, 0, 4, ptr(sp.sample_seg_off), ptr(p.rows_of_sample), 0,  # noqa: E731
-                                          ptr(gam), ptr(bet), B, 32, 1e-5, 1e-5, ptr(scale), ptr(shift), stream()))
+    scratch = torch.empty(B * 8 * c, dtype=torch.float64, device='cuda')
+    ticket = torch.zeros(64, dtype=torch.int32, device='cuda')
+    fi = lambda: check(lib.of_gn_finalize(ptr(part), c, 4, None, 0, 4, ptr(sp.sample_seg_off), sp.n_seg, ptr(p.rows_of_sample), 0,  # noqa: E731
+                                          ptr(gam), ptr(bet), B, 32, 1e-5, 1e-5, ptr(scale), ptr(shift), ptr(scratch), ptr(ticket),
+                                          stream()))
     ap = lambda: check(lib.of_gn_apply(ptr(x0), x0.stride(0), c0, a1[0], a1[1], a1[2], ptr(p.batch_id), 0, n, ptr(scale),  # noqa: E731
                                        ptr(shift), 1, dt(x0), ptr(out), out.stride(0), 0, stream()))
     ts, tf, ta = timed(st), timed(fi), timed(ap)
