@@ -9,7 +9,7 @@
 // The im2col buffer is never written to HBM: gather warps build each [128 x 64] bf16 A tile
 // directly in shared memory, in the 128-byte-swizzled K-major layout tcgen05.mma reads.
 //
-// One persistent CTA per SM, 512 threads, warp-specialised (role -> warp id: see TC_WARP_* below):
+// One persistent CTA per SM, 512 threads, warp-specialised (role -> warp id: tc_roles() below; the default layout is):
 //   warps 0-3   epilogue: tcgen05.ld of the fp32 accumulator, +bias/+emb[batch]/+residual, store; optionally the
 //               group-norm partial statistics of the tile (warp-shuffle reduction, one write per 32-row chunk --
 //               no atomics, bit-reproducible): the statistics pass of the following DualOctreeGroupNorm
@@ -43,16 +43,19 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
 constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_PROD_WARPS = 8;
-// Warp roles, ordered by scheduling priority: the SM's warp schedulers prefer the HIGHEST warp id among the eligible
-// warps of a sub-partition (measured, B300_MICROARCH.md), so the latency-critical roles sit at the top and the pollers
-// at the bottom -- with the epilogue at warps 0-3 below eight busy producers it ran at ~0.05 IPC and became the
-// bottleneck of the short-K layers (profiles/tc_gather_experiments_r02.md).  The epilogue warp e must satisfy
-// warp_id % 4 == e (TMEM lane quarter).
-constexpr int TC_WARP_SCOUT = 0;                                       // polls the full barriers for the MMA warp
-constexpr int TC_WARP_PROD0 = 1;                                       // warps 1..8: gather producers
-constexpr int TC_WARP_LOADER = 10;                                     // (warp 9 idles)
-constexpr int TC_WARP_MMA = 11;
-constexpr int TC_WARP_EPI0 = 12;                                       // warps 12..15
+// Warp roles.  The SM's warp schedulers prefer the HIGHEST warp id among the eligible warps of a sub-partition
+// (measured, B300_MICROARCH.md), so the order of the roles is a scheduling-priority choice; which order is best was
+// settled by measurement (profiles/tc_gather_experiments_r02.md), hence a run-time layout id (TcParams::layout):
+//   0: epilogue 0-3 | MMA 4 | loader 5 | producers 6-13 | scout 14            (producers on top)
+//   1: idle 0 | scout 1 | loader 2 | MMA 3 | producers 4-11 | epilogue 12-15   (epilogue on top, then producers)
+//   2: scout 0 | producers 1-8 | idle 9 | loader 10 | MMA 11 | epilogue 12-15  (latency-critical roles on top)
+// An epilogue warp e must satisfy warp_id % 4 == e (TMEM lane quarter), which all three respect.
+struct TcRoles { int scout, prod0, loader, mma, epi0; };
+__device__ __forceinline__ TcRoles tc_roles(int layout) {
+  if (layout == 1) return TcRoles{1, 4, 2, 3, 12};
+  if (layout == 2) return TcRoles{0, 1, 10, 11, 12};
+  return TcRoles{14, 6, 5, 4, 0};
+}
 constexpr int TC_THREADS = 16 * 32;                                    // 512
 constexpr int TC_MAX_TAPS = 27;
 constexpr int TC_GROUPS = 4;                // producer groups of 2 warps
@@ -89,6 +92,18 @@ __device__ __forceinline__ uint32_t ld_acquire_cta(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
+}
+// the same with cluster-scope acquire (the arrivals come from the peer CTA)
+__device__ __forceinline__ bool mbar_test_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 // non-blocking probe of a phase (true = the phase with this parity has completed)
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
@@ -350,6 +365,7 @@ struct TcParams {
   int cblocks;       // (c0+c1)/64
   int npad;          // N rounded up to 16 (rows per K block in the packed weight image)
   int m_tiles, n_tiles;   // m_tiles counts CTA tiles of 128*MT rows
+  int layout;        // warp-role layout id (tc_roles)
   int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA, 32 no tap-table reads
   unsigned long long* trace;   // of_tc_trace_set: per-role clock64 stamps of one CTA (diagnostics), or NULL
   int trace_cap, trace_block;
@@ -401,10 +417,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   const uint32_t tmem_slot = bar_tempty + 16;
   // per ring slot: number of completed fills, published by the scout warp (A slots: 16 words, B slots: 4 words)
   const uint32_t flag_a = aux + 384, flag_b = aux + 448;
-  const uint32_t pflag_a = aux + 512, pflag_b = aux + 576;   // CG = 2, leader: the PEER's counts (written remotely)
+  // CG = 2, leader: "the peer's stage is full" barriers, one per ring slot (the peer's scout arrives remotely)
+  const uint32_t bar_pfull = aux + 512, bar_pbfull = aux + 640;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::RING_BYTES + 352);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcRoles W = tc_roles(p.layout);
   const of_gemm_args& g = p.g;
   const int taps = g.taps;
   // work items: CTA tiles of 128*MT rows (CG = 1) or pair tiles of 256 rows that both CTAs of a pair walk together
@@ -416,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   constexpr int TILE_ROWS = TC_BM * MT * CG;
   const bool tr = p.trace != nullptr && (int)blockIdx.x == p.trace_block;
 
-  if (warp == TC_WARP_MMA && lane == 0) {
+  if (warp == W.mma && lane == 0) {
     for (int s = 0; s < Cfg::A_STAGES; ++s) {
       // every producer thread of the stage's sub-tiles (+ the weight loader's expect_tx arrival when the ring is shared)
       mbar_init(bar_full + 8 * s, SUBS * (TC_PROD_WARPS / TC_GROUPS) * 32 + (UNI ? 1 : 0));
@@ -431,10 +449,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       mbar_init(bar_tempty + 8 * a, CG * TC_EPI_WARPS * 32);      // CG = 2: the epilogues of both CTAs
     }
     for (int i = 0; i < 20; ++i) st_release_cta(flag_a + 4 * i, 0u);
-    for (int i = 0; i < 20; ++i) st_release_cta(pflag_a + 4 * i, 0u);
+    if constexpr (CG == 2) {
+      for (int s = 0; s < Cfg::A_STAGES; ++s) mbar_init(bar_pfull + 8 * s, 1);
+      for (int s = 0; s < Cfg::B_STAGES; ++s) mbar_init(bar_pbfull + 8 * s, 1);
+    }
     fence_mbar_init();
   }
-  if (warp == TC_WARP_MMA) {                               // CG = 2: the same warp of BOTH CTAs issues the paired alloc
+  if (warp == W.mma) {                                     // CG = 2: the same warp of BOTH CTAs issues the paired alloc
     if constexpr (CG == 2) tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
     else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   }
@@ -444,9 +465,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  if (warp >= TC_WARP_EPI0) {
+  if (warp >= W.epi0 && warp < W.epi0 + TC_EPI_WARPS) {
     // =========================== epilogue ===========================
-    const int ew = warp - TC_WARP_EPI0;                      // 0..3 = TMEM lane quarter (= warp id % 4)
+    const int ew = warp - W.epi0;                      // 0..3 = TMEM lane quarter (= warp id % 4)
     const int r = ew * 32 + lane;
     int it = 0, tn = 0;
     for (int tile = w_first; tile < total_tiles; tile += w_stride, ++it) {
@@ -642,7 +663,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       else mbar_arrive(bar_tempty + 8 * as);
       if (ew == 0 && lane == 0) trace_put(p, 6, tn, tr);
     }
-  } else if (warp == TC_WARP_MMA) {
+  } else if (warp == W.mma) {
    if (CG == 1 || rank == 0) {
     // =========================== MMA issuer ===========================
     // Issuing is nearly synchronous with execution (the tensor pipe accepts only a few MMAs ahead), so every cycle this
@@ -661,15 +682,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
       for (int kb = 0; kb < p.num_kb; kb += KSUB) {
         {
-          // ready = the slot's fill count has passed the number of fills already consumed -- in this CTA and, for a
-          // pair, in the peer (whose scout writes its counts into this CTA's shared memory)
+          // ready = the slot's fill count has passed the number of fills already consumed (for a pair the leader's scout
+          // counts a fill only when the peer has signalled its half as well)
           auto ready = [&]() {
-            uint32_t fa = CG == 2 ? ld_acquire_cluster(flag_a + 4 * stage) : ld_acquire_cta(flag_a + 4 * stage);
-            uint32_t fb = UNI ? ~0u : (CG == 2 ? ld_acquire_cluster(flag_b + 4 * bstage) : ld_acquire_cta(flag_b + 4 * bstage));
-            if constexpr (CG == 2) {
-              fa = min(fa, ld_acquire_cluster(pflag_a + 4 * stage));
-              if (!UNI) fb = min(fb, ld_acquire_cluster(pflag_b + 4 * bstage));
-            }
+            const uint32_t fa = ld_acquire_cta(flag_a + 4 * stage);
+            const uint32_t fb = UNI ? ~0u : ld_acquire_cta(flag_b + 4 * bstage);
             return fa > round && (UNI || fb > bround);
           };
           if (!ready()) {
@@ -725,7 +742,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
       }
     }
    }
-  } else if (warp == TC_WARP_SCOUT) {
+  } else if (warp == W.scout) {
     // =========================== scout ===========================
     // One lane per ring slot (lanes 0..A_STAGES-1: gathered tiles, lanes 16..: weight tiles) polls its slot's full
     // barrier with the non-blocking mbarrier.test_wait -- all slots in one instruction -- and publishes the number of
@@ -739,16 +756,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
     const uint32_t slot = is_a ? lane : lane - 16;
     const uint32_t my_total = (is_a || is_b) ? (total_stages + nslots - 1 - slot) / nslots : 0u;
     const uint32_t bar = is_a ? bar_full + 8 * slot : bar_bfull + 8 * slot;
-    // the peer of a pair publishes into the LEADER's shared memory (its own MMA warp issues nothing)
-    const uint32_t flag = (CG == 2 && rank != 0) ? map_to_cta(is_a ? pflag_a + 4 * slot : pflag_b + 4 * slot, 0)
-                                                 : (is_a ? flag_a + 4 * slot : flag_b + 4 * slot);
+    const uint32_t flag = is_a ? flag_a + 4 * slot : flag_b + 4 * slot;
+    // pair: the peer's scout forwards each completed fill to the leader's bar_pfull / bar_pbfull (remote mbarrier
+    // arrive); the leader's scout counts a fill when both its own stage and the peer's have landed
+    const uint32_t pbar = is_a ? bar_pfull + 8 * slot : bar_pbfull + 8 * slot;
+    const uint32_t pbar_remote = CG == 2 ? map_to_cta(pbar, 0) : 0u;
     uint32_t done = 0, phase = 0;
     const long long t0 = clock64();
     while (__any_sync(0xffffffffu, done < my_total)) {
-      if (done < my_total && mbar_test_wait(bar, phase)) {
+      bool ok = done < my_total && mbar_test_wait(bar, phase);
+      if (CG == 2 && rank == 0 && ok) ok = mbar_test_wait_cluster(pbar, phase);
+      if (ok) {
         ++done; phase ^= 1u;
-        if (CG == 2 && rank != 0) st_release_cluster(flag, done);
-        else if (CG == 2) asm volatile("st.release.cluster.shared::cta.u32 [%0], %1;" ::"r"(flag), "r"(done) : "memory");
+        if (CG == 2 && rank != 0) mbar_arrive_cluster(pbar_remote);
         else st_release_cta(flag, done);
       }
       else __nanosleep(64);                                 // nothing landed: leave the issue slots to the working warps
@@ -757,7 +777,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         __trap();
       }
     }
-  } else if (warp == TC_WARP_LOADER) {
+  } else if (warp == W.loader) {
     // =========================== weight loader ===========================
     constexpr int NST = UNI ? Cfg::A_STAGES : Cfg::B_STAGES;
     int stage = 0, tn = 0;
@@ -785,12 +805,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= TC_WARP_PROD0 && warp < TC_WARP_PROD0 + TC_PROD_WARPS) {
+  } else if (warp >= W.prod0 && warp < W.prod0 + TC_PROD_WARPS) {
     // =========================== gather producers ===========================
     // 4 independent groups of 2 warps; group g produces the 16 KB sub-tiles whose running index is = g mod 4, so 4
     // sub-tiles (64 KB of gathers) are in flight per SM and the memory latency of one is hidden behind the other three.
     // Each thread owns one 16-byte chunk column (q) of 16 rows.
-    const int pt = threadIdx.x - TC_WARP_PROD0 * 32;                // 0..255
+    const int pt = threadIdx.x - W.prod0 * 32;                      // 0..255
     const int grp = pt >> 6;                                        // producer group 0..3
     const int gt = pt & 63;
     const int q = gt & 7;                                           // 16-byte chunk of the 128-byte row
@@ -931,7 +951,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
   tc_fence_before();
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();               // no remote arrive / store may hit a CTA that has exited
-  if (warp == TC_WARP_MMA) {
+  if (warp == W.mma) {
     tc_fence_after();
     if constexpr (CG == 2) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
     else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -969,7 +989,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int taps, int
 }
 
 
-static int g_mt = -1, g_uni = -1, g_cg = -1;               // kernel variant switches (of_tc_config / environment)
+static int g_mt = -1, g_uni = -1, g_cg = -1, g_layout = -1;   // kernel variant switches (of_tc_config / environment)
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cap = 0, g_trace_block = 0;
 
@@ -1057,11 +1077,13 @@ extern "C" int of_pack_weight_tc(const float* w_canonical, int32_t taps, int32_t
   return OF_OK;
 }
 
-extern "C" int of_tc_config(int32_t mt, int32_t uni, int32_t cg) {
+extern "C" int of_tc_config(int32_t mt, int32_t uni, int32_t cg, int32_t layout) {
   if (g_mt < 0) { g_mt = env_int("OCTFUSION_TC_MT", 2); g_uni = env_int("OCTFUSION_TC_UNI", 0); g_cg = env_int("OCTFUSION_TC_CG", 1); }
+  if (g_layout < 0) g_layout = env_int("OCTFUSION_TC_LAYOUT", 0);
   if (mt == 1 || mt == 2) g_mt = mt;
   if (uni == 0 || uni == 1) g_uni = uni;
   if (cg == 1 || cg == 2) g_cg = cg;
+  if (layout >= 0 && layout <= 2) g_layout = layout;
   return OF_OK;
 }
 
@@ -1104,6 +1126,8 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
     p.debug = dbg;
   }
   p.trace = g_trace; p.trace_cap = g_trace_cap; p.trace_block = g_trace_block;
+  if (g_layout < 0) g_layout = env_int("OCTFUSION_TC_LAYOUT", 0);
+  p.layout = g_layout;
   p.cblocks = (a.c0 + a.c1) / 64;
   p.num_kb = p.cblocks * a.taps + (a.ntype > 0 ? 1 : 0);
   p.npad = (a.N + 15) / 16 * 16;

@@ -42,8 +42,23 @@ class HRStepper:
         self.label = label
         self.eps = None
         self.graph = None
+        self._graph_key = None
         self.use_cuda_graph = use_cuda_graph
         self.kernels_per_step = 0
+
+    def _weights_key(self):
+        """fingerprint of every parameter of the two nets: the captured graph bakes in device copies of the weights
+        (packed tcgen05 images, concatenated embedding projections, padded first conv), so an in-place update, a
+        load_state_dict or an EMA swap must force a re-capture"""
+        key = []
+        for net in (self.hr, self.lr):
+            if net is not None:
+                key += [(p.data_ptr(), p._version) for p in net.parameters()]
+        return tuple(key)
+
+    def invalidate(self):
+        """drop the captured CUDA graph (next step re-captures it)"""
+        self.graph, self._graph_key = None, None
 
     def set_latent(self, x):
         self.x.copy_(x)
@@ -72,6 +87,8 @@ class HRStepper:
             self._body()
             self.kernels_per_step = _lib.launch_count() - c0
             return
+        if self.graph is not None and self._graph_key != self._weights_key():
+            self.invalidate()                    # weights changed since capture: the graph holds stale packed copies
         if self.graph is None:
             # eager warm-up on a side copy of the state (builds packed weights, tables, func attributes)
             keep = self.x.clone()
@@ -83,6 +100,7 @@ class HRStepper:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._body()
+            self._graph_key = self._weights_key()
             self.set_latent(keep)        # capture does not execute; restore is a no-op safety
         self.graph.replay()
 
@@ -91,6 +109,12 @@ class HRStepper:
 def sample_loop(unet_hr, unet_lr, doctree, ddim_steps=200, label=None, noise=None, seed=0,
                 act_dtype=torch.bfloat16, use_cuda_graph=True, stepper=None):
     """Returns the denoised latent [total_num, code_channel] fp32 (reference :300-352, 'eps' branch)."""
+    if stepper is not None:
+        # a caller-provided stepper carries its own label / dtype / graph switch: refuse silently different arguments
+        same_label = (label is None and stepper.label is None) or (label is not None and stepper.label is not None
+                                                                   and torch.equal(label.to(stepper.label.device), stepper.label))
+        if stepper.act_dtype != act_dtype or not same_label or stepper.doctree is not doctree:
+            raise ValueError('sample_loop: the stepper was built for another doctree / label / act_dtype')
     st = stepper or HRStepper(unet_hr, unet_lr, doctree, act_dtype, label, use_cuda_graph)
     if noise is None:
         g = torch.Generator(device=doctree.device).manual_seed(seed)

@@ -108,9 +108,9 @@ def test_graphconv_bf16_simt_equals_tc():
 def pair_variant():
     """run the tcgen05 GEMM's 256-wide tiles as CTA pairs (tcgen05.mma.cta_group::2) for the duration of a test"""
     from octfusion_b200._lib import lib
-    lib.of_tc_config(-1, -1, 2)
+    lib.of_tc_config(-1, -1, 2, -1)
     yield
-    lib.of_tc_config(-1, -1, 1)
+    lib.of_tc_config(-1, -1, 1, -1)
 
 
 @pytest.mark.parametrize('d,cin,cout,nt', [(4, 256, 512, 3), (5, 128, 256, 4), (6, 128, 256, 5), (5, 768, 256, 4)])
@@ -137,7 +137,7 @@ def test_cta_pair_equals_single_cta_bitwise(pair_variant):
     emb = _rand((3, cout), 5).to(DEV)
     run = lambda: conv.run(x, plan, row_add=emb, row_add_idx=plan.batch_id, resid=res, stats=plan.stat)  # noqa: E731
     a = run()
-    lib.of_tc_config(-1, -1, 1)
+    lib.of_tc_config(-1, -1, 1, -1)
     b = run()
     assert torch.equal(a, b) and torch.equal(a._of_stats.part, b._of_stats.part)
 

@@ -244,3 +244,28 @@ def test_stage1_sample_loop_x0_branch(uncond):
 def F_conv_in(inp, sd):
     """input_emb of the stand-alone LR net applied to (x | x_self_cond) (graph_unet_lr.py:198-200)."""
     return torch.nn.functional.conv3d(inp, sd['unet_lr.input_emb.weight'], sd['unet_lr.input_emb.bias'], padding=1)
+
+
+def test_stepper_recaptures_when_weights_change():
+    """The captured CUDA graph holds packed copies of the weights; an in-place parameter update must invalidate it
+    (ADVICE round 1): the next replay equals an eager step with the new weights, not the stale graph."""
+    from octfusion_b200.sampler import HRStepper, sampling_log_snr
+    cfg = SMALL
+    sd = R.seeded_state_dict(model_shapes(cfg), 2)
+    net = build_product(cfg, sd)
+    doc = product_doctree(1, 0)
+    ls = sampling_log_snr(4)
+    noise = _rand((doc.total_num, 3), 9).to(DEV)
+
+    def one_step(use_graph, stepper=None):
+        st = stepper or HRStepper(net.unet_hr, net.unet_lr, doc, torch.float32, None, use_cuda_graph=use_graph)
+        st.set_latent(noise)
+        st.step(ls[0], ls[1])
+        return st, st.x.clone()
+    st, a = one_step(True)
+    with torch.no_grad():
+        net.unet_hr.out.weights.mul_(1.5)                   # in-place: bumps the parameter's version
+    _, b_graph = one_step(True, st)                          # same stepper: must notice and re-capture
+    _, b_eager = one_step(False)
+    assert not torch.equal(a, b_graph)
+    assert torch.equal(b_graph, b_eager)
