@@ -49,7 +49,7 @@ int of_abi_sizeof_octree_levels(void);
 int of_tc_trace_set(void* buf, int32_t cap_per_region, int32_t block);
 /* kernel-variant switches of of_gather_gemm_tc (experiments / tests; a value outside the set keeps the current one):
  * mt in {1, 2}: 128-row tiles per CTA for N <= 128; uni in {0, 1}: weight tile inside the gather ring's stage;
- * cg in {1, 2}: 2 = CTA pairs (tcgen05 cta_group::2) for the 256-wide tiles; layout in {0, 1, 2}: order of the warp
+ * cg in {1, 2}: 2 = CTA pairs (tcgen05 cta_group::2) for the 256-wide tiles; layout in {0, 1}: order of the warp
  * roles (scheduling priority follows the warp id).  Defaults: environment OCTFUSION_TC_MT / _UNI / _CG / _LAYOUT, else
  * 2 / 0 / 1 / 0. */
 int of_tc_config(int32_t mt, int32_t uni, int32_t cg, int32_t layout);
