@@ -41,20 +41,21 @@ namespace of {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
-constexpr int TC_EPI_WARPS = 8;                   // two per TMEM lane quarter (each takes alternate column chunks)
+constexpr int TC_EPI_WARPS = 4;                   // (8 = two per TMEM lane quarter was measured: no faster -- the drain is paced by TMEM reads)
 constexpr int TC_PROD_WARPS = 8;
 // Warp roles.  The SM's warp schedulers prefer the HIGHEST warp id among the eligible warps of a sub-partition
 // (measured, B300_MICROARCH.md), so the order of the roles is a scheduling-priority choice; which order is best was
 // settled by measurement (profiles/tc_gather_experiments_r02.md), hence a run-time layout id (TcParams::layout):
-//   0: epilogue 0-7 | MMA 8 | loader 9 | producers 10-17 | scout 18            (producers on top)
-//   1: idle 0 | scout 1 | loader 2 | MMA 3 | producers 4-11 | epilogue 12-19   (epilogue on top, then producers)
+//   0: epilogue 0-3 | MMA 4 | loader 5 | producers 6-13 | scout 14            (producers on top)
+//   1: idle 0 | scout 1 | loader 2 | MMA 3 | producers 4-11 | epilogue 12-15   (epilogue on top, then producers)
+// (measured identical: profiles/tc_gather_experiments_r02.md)
 // An epilogue warp e works on TMEM lane quarter e % 4, which must equal warp_id % 4: both layouts respect it.
 struct TcRoles { int scout, prod0, loader, mma, epi0; };
 __device__ __forceinline__ TcRoles tc_roles(int layout) {
   if (layout == 1) return TcRoles{1, 4, 2, 3, 12};
-  return TcRoles{18, 10, 9, 8, 0};
+  return TcRoles{14, 6, 5, 4, 0};
 }
-constexpr int TC_THREADS = 20 * 32;                                    // 640
+constexpr int TC_THREADS = 16 * 32;                                    // 512
 constexpr int TC_MAX_TAPS = 27;
 constexpr int TC_GROUPS = 4;                // producer groups of 2 warps
 
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 
   if (warp >= W.epi0 && warp < W.epi0 + TC_EPI_WARPS) {
     // =========================== epilogue ===========================
-    const int ew = warp - W.epi0;                        // 0..7
+    const int ew = warp - W.epi0;                        // 0..TC_EPI_WARPS-1
     const int qw = ew & 3, chalf = ew >> 2;              // TMEM lane quarter (= warp id % 4) | which column chunks
     const int r = qw * 32 + lane;
     int it = 0, tn = 0;
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         // two TMEM loads in flight per iteration: the epilogue is latency-bound (tcgen05.ld -> wait -> stores), not
         // issue-bound, and with the MMA warp no longer waiting on barriers a short-K tile leaves it ~8k cycles
 #pragma unroll 1
-        for (int c0 = chalf * 2 * CH; c0 < BN; c0 += 4 * CH) {          // the quarter's other warp takes the chunks between
+        for (int c0 = chalf * 2 * CH; c0 < BN; c0 += (TC_EPI_WARPS / 4) * 2 * CH) {   // (with 8 warps the quarter's other warp takes the chunks between)
           uint32_t accA[32], accB[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)((as * MT + h) * BN + c0);
           const bool pair = c0 + CH < BN;
@@ -1080,7 +1081,7 @@ extern "C" int of_pack_weight_tc(const float* w_canonical, int32_t taps, int32_t
 }
 
 extern "C" int of_tc_config(int32_t mt, int32_t uni, int32_t cg, int32_t layout) {
-  if (g_mt < 0) { g_mt = env_int("OCTFUSION_TC_MT", 2); g_uni = env_int("OCTFUSION_TC_UNI", 0); g_cg = env_int("OCTFUSION_TC_CG", 1); }
+  if (g_mt < 0) { g_mt = env_int("OCTFUSION_TC_MT", 2); g_uni = env_int("OCTFUSION_TC_UNI", 1); g_cg = env_int("OCTFUSION_TC_CG", 1); }
   if (g_layout < 0) g_layout = env_int("OCTFUSION_TC_LAYOUT", 0);
   if (mt == 1 || mt == 2) g_mt = mt;
   if (uni >= 0 && uni <= 2) g_uni = uni;
@@ -1136,7 +1137,7 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // experiment switches (tools/exp_tc.sh): OCTFUSION_TC_MT = row tiles per CTA for the narrow layers (1 | 2),
   // OCTFUSION_TC_UNI = 1: weight tile in the gather ring's stage (one barrier pair per stage)
-  if (g_mt < 0) { g_mt = env_int("OCTFUSION_TC_MT", 2); g_uni = env_int("OCTFUSION_TC_UNI", 0); g_cg = env_int("OCTFUSION_TC_CG", 1); }
+  if (g_mt < 0) { g_mt = env_int("OCTFUSION_TC_MT", 2); g_uni = env_int("OCTFUSION_TC_UNI", 1); g_cg = env_int("OCTFUSION_TC_CG", 1); }
   const int mt = g_mt, uni = g_uni;
   // widest tile that divides the padded N: fewer re-gathers of A per output column
   if (p.npad % 256 == 0) {
