@@ -490,6 +490,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         const float* radd = (row_ok && g.row_add) ? g.row_add + (int64_t)g.row_add_idx[m] * g.ld_row_add : nullptr;
         const __nv_bfloat16* res =
             (row_ok && g.resid) ? reinterpret_cast<const __nv_bfloat16*>(g.resid) + (int64_t)m * g.ld_resid : nullptr;
+        // ---- group-norm partial statistics of this 32-row chunk (see of_gemm_args.stat_out); set up first so that its
+        // index loads are in flight together with those of the staging below ----
+        int seg0 = 0, nseg = 0, my_seg = 0, my_slot = 0;
+        if (g.stat_out != nullptr) {
+          const int chunk = (mt0 + h * TC_BM) / 32 + qw;
+          if (chunk * 32 < g.M) {
+            seg0 = __ldg(g.stat_chunk_seg + chunk);
+            nseg = __ldg(g.stat_chunk_seg + chunk + 1) - seg0;
+            if (lane < nseg) my_slot = __ldg(g.stat_seg_slot + seg0 + lane);   // lane s: slot of the chunk's segment s
+            if (nseg > 1) {                                // rows of several samples in this chunk: rank of my sample run
+              const int b = row_ok ? (g.stat_sample ? __ldg(g.stat_sample + m) : m / g.stat_rows_per_sample) : -1;
+              const int bp = __shfl_up_sync(0xffffffffu, b, 1);
+              const unsigned chg = __ballot_sync(0xffffffffu, lane > 0 && row_ok && b != bp);
+              my_seg = __popc(chg & (0xffffffffu >> (31 - lane)));
+            }
+          }
+        }
         // ---- per-column addends (bias + emb[batch]): when the 32 rows of this warp share one sample -- nearly always --
         // the BN-wide row is staged ONCE per row tile in the warp's shared-memory slot and read back as broadcast
         // ld.shared.v4 per chunk; per-row global loads (L2 latency on every chunk: the 13 KB of L1 left beside the rings
@@ -517,25 +534,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
             __syncwarp();
           }
         }
-        // ---- group-norm partial statistics of this 32-row chunk (see of_gemm_args.stat_out) ----
-        int seg0 = 0, nseg = 0, my_seg = 0, my_slot = 0;
-        if (g.stat_out != nullptr) {
-          const int chunk = (mt0 + h * TC_BM) / 32 + qw;
-          if (chunk * 32 < g.M) {
-            seg0 = __ldg(g.stat_chunk_seg + chunk);
-            nseg = __ldg(g.stat_chunk_seg + chunk + 1) - seg0;
-            if (lane < nseg) my_slot = __ldg(g.stat_seg_slot + seg0 + lane);   // lane s: slot of the chunk's segment s
-            if (nseg > 1) {                                // rows of several samples in this chunk: rank of my sample run
-              const int b = row_ok ? (g.stat_sample ? __ldg(g.stat_sample + m) : m / g.stat_rows_per_sample) : -1;
-              const int bp = __shfl_up_sync(0xffffffffu, b, 1);
-              const unsigned chg = __ballot_sync(0xffffffffu, lane > 0 && row_ok && b != bp);
-              my_seg = __popc(chg & (0xffffffffu >> (31 - lane)));
-            }
-          }
-        }
         constexpr int CH = BN >= 32 ? 32 : 16;
         // one 32-column chunk of my row: accumulators -> (+bias, +emb, +residual) -> store (+ norm statistics)
-        auto process = [&](uint32_t (&acc)[32], int c0) {
+        // residual rows are fetched BEFORE the wait on the TMEM load (ncu: the exposed latency of these four 16-byte
+        // loads per chunk was the largest stall of the epilogue warps)
+        const bool res_vec = g.resid != nullptr && (g.ld_resid % 8 == 0) && n0 + BN <= g.N &&
+                             (reinterpret_cast<uintptr_t>(g.resid) % 16 == 0);
+        auto process = [&](uint32_t (&acc)[32], int c0, const uint4 (&rpre)[4]) {
           const int nb = n0 + c0;
           float v[32];
 #pragma unroll
@@ -578,7 +583,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
               }
             }
             if (res) {
-              if (full && (g.ld_resid % 8 == 0)) {
+              if (res_vec) {
+#pragma unroll
+                for (int q = 0; q < CH / 8; ++q) {
+                  float f[8];
+                  bf16x8_to_f32(rpre[q], f);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+                }
+              } else if (full && (g.ld_resid % 8 == 0)) {
 #pragma unroll
                 for (int q = 0; q < CH / 8; ++q) {
                   float f[8];
@@ -657,10 +670,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           const bool pair = c0 + CH < BN;
           if (CH == 32) { OF_TMEM_LD32(taddr, accA); if (pair) { OF_TMEM_LD32(taddr + CH, accB); } }
           else { OF_TMEM_LD16(taddr, accA); if (pair) { OF_TMEM_LD16(taddr + CH, accB); } }
+          uint4 rA[4], rB[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { rA[q] = make_uint4(0u, 0u, 0u, 0u); rB[q] = make_uint4(0u, 0u, 0u, 0u); }
+          if (res_vec && res != nullptr) {
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) {
+              rA[q] = ldg_nc_v4(res + n0 + c0 + q * 8);
+              if (pair) rB[q] = ldg_nc_v4(res + n0 + c0 + CH + q * 8);
+            }
+          }
           tmem_ld_wait();
           if (p.debug & 4) continue;
-          process(accA, c0);
-          if (pair) process(accB, c0 + CH);
+          process(accA, c0, rA);
+          if (pair) process(accB, c0 + CH, rB);
         }
       }
       tc_fence_before();
