@@ -536,11 +536,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         }
         constexpr int CH = BN >= 32 ? 32 : 16;
         // one 32-column chunk of my row: accumulators -> (+bias, +emb, +residual) -> store (+ norm statistics)
-        // residual rows are fetched BEFORE the wait on the TMEM load (ncu: the exposed latency of these four 16-byte
-        // loads per chunk was the largest stall of the epilogue warps)
-        const bool res_vec = g.resid != nullptr && (g.ld_resid % 8 == 0) && n0 + BN <= g.N &&
-                             (reinterpret_cast<uintptr_t>(g.resid) % 16 == 0);
-        auto process = [&](uint32_t (&acc)[32], int c0, const uint4 (&rpre)[4]) {
+        auto process = [&](uint32_t (&acc)[32], int c0) {
           const int nb = n0 + c0;
           float v[32];
 #pragma unroll
@@ -583,15 +579,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
               }
             }
             if (res) {
-              if (res_vec) {
-#pragma unroll
-                for (int q = 0; q < CH / 8; ++q) {
-                  float f[8];
-                  bf16x8_to_f32(rpre[q], f);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
-                }
-              } else if (full && (g.ld_resid % 8 == 0)) {
+              if (full && (g.ld_resid % 8 == 0)) {
 #pragma unroll
                 for (int q = 0; q < CH / 8; ++q) {
                   float f[8];
@@ -670,20 +658,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
           const bool pair = c0 + CH < BN;
           if (CH == 32) { OF_TMEM_LD32(taddr, accA); if (pair) { OF_TMEM_LD32(taddr + CH, accB); } }
           else { OF_TMEM_LD16(taddr, accA); if (pair) { OF_TMEM_LD16(taddr + CH, accB); } }
-          uint4 rA[4], rB[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { rA[q] = make_uint4(0u, 0u, 0u, 0u); rB[q] = make_uint4(0u, 0u, 0u, 0u); }
-          if (res_vec && res != nullptr) {
-#pragma unroll
-            for (int q = 0; q < CH / 8; ++q) {
-              rA[q] = ldg_nc_v4(res + n0 + c0 + q * 8);
-              if (pair) rB[q] = ldg_nc_v4(res + n0 + c0 + CH + q * 8);
-            }
-          }
           tmem_ld_wait();
           if (p.debug & 4) continue;
-          process(accA, c0, rA);
-          if (pair) process(accB, c0 + CH, rB);
+          process(accA, c0);
+          if (pair) process(accB, c0 + CH);
         }
       }
       tc_fence_before();

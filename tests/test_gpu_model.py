@@ -69,6 +69,7 @@ def test_lr_middle(uncond, dtype, tol):
     ts = torch.tensor([1.5, -0.5])
     ref = R.lr_forward_as_middle(h, dg, ts, sd, lr_cfg)
     y = net.unet_lr.forward_as_middle(h.to(DEV).to(dtype), doc, ts.to(DEV), None, None).float().cpu()
+    print('ERR lr_middle %s max %.3e l2 %.3e' % (str(dtype), relerr(y, ref), float((y - ref).norm() / ref.norm())))
     assert relerr(y, ref) < tol
     if dtype == torch.bfloat16:
         assert float((y - ref).norm() / ref.norm()) < 2.5e-2
@@ -91,6 +92,7 @@ def test_full_unet_forward(cfg_name, dtype, tol):
             label=label.to(DEV) if label is not None else None)
     assert y.dtype == torch.float32
     e = relerr(y.cpu(), ref)
+    print('ERR full_unet %s %s %.3e' % (cfg_name, str(dtype), e))
     assert e < tol, e
 
 
@@ -141,6 +143,7 @@ def test_sampler_cuda_graph_matches_eager_and_oracle():
                         use_cuda_graph=graph)
         assert relerr(y.cpu(), x) < 2e-3, (graph, relerr(y.cpu(), x))
     yb = sample_loop(net.unet_hr, net.unet_lr, doc, ddim_steps=steps, noise=noise.to(DEV), act_dtype=torch.bfloat16)
+    print('ERR sampler4 bf16 %.3e' % relerr(yb.cpu(), x))
     assert relerr(yb.cpu(), x) < 4e-2
 
 
@@ -166,6 +169,7 @@ def test_unet_against_reference_golden(name, dtype, tol):
     label = torch.tensor(UNET_LABEL)[:batch].to(DEV) if cfg.get('num_classes') else None
     y = net(unet_type='hr', x=x.to(DEV).to(dtype), doctree=doc, timesteps=ts.to(DEV), unet_lr=net.unet_lr, label=label)
     e = relerr(y.cpu(), torch.from_numpy(g['y']))
+    print('ERR golden %s %s %.3e' % (name, str(dtype), e))
     assert e < tol, e
 
 
@@ -202,6 +206,7 @@ def test_lr_unet_standalone_stage1(uncond, dtype, tol):
     ref = R.lr_forward_dense(x, ts, sd, lr_cfg, as_middle=False)
     y = net(unet_type='lr', x=x.to(DEV).to(dtype), timesteps=ts.to(DEV))
     assert y.shape == ref.shape
+    print('ERR lr_standalone %s %.3e' % (str(dtype), relerr(y.float().cpu(), ref)))
     assert relerr(y.float().cpu(), ref) < tol
 
 
