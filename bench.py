@@ -520,7 +520,7 @@ def run_ours(args):
             'roofline': roofline, 'cpu_baseline': cpu, 'library_baseline': library,
             'gathered_latent_rows': [int(t.shape[0]) for t in gathered]}
     if per_layer:
-        line['roofline_per_layer'] = per_layer[:14]
+        line['roofline_per_layer'] = per_layer[:40]
     os.write(real_stdout, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
