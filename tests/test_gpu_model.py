@@ -54,12 +54,11 @@ def test_resblock_and_resample(uncond, dtype, tol):
     assert relerr(y.float().cpu(), ref) < tol
 
 
-# The LR middle block alone is an *intermediate* (post-GroupNorm+SiLU features after ~20 bf16 stages).  In bf16 its
-# max-norm error is noise dominated: the norm statistics use floating-point atomics, and a one-ulp change is amplified
-# by every bf16 rounding that follows, so the worst element of 0.5 M moves between 2 % and 3.5 % from run to run
-# (tools/lr_bf16_err.py).  The stable quantity -- relative L2 error, ~1.6 % -- is asserted at 2.5e-2, the max-norm at
-# 6e-2; the north-star 2e-2 max-norm tolerance is asserted on the U-Net OUTPUT below.
-@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-4), (torch.bfloat16, 6e-2)])
+# The LR middle block alone is an *intermediate* (post-GroupNorm+SiLU features after ~20 bf16 stages).  Since round 2 the
+# norm statistics are deterministic (no atomics), so its bf16 error is a fixed number: max-norm 2.2e-2, relative L2 1.6e-2
+# (round 1: 2 % .. 3.5 % from run to run, asserted at 6e-2).  The north-star 2e-2 max-norm tolerance is asserted on the U-Net
+# OUTPUT below; the intermediate is held to 2.5e-2 max-norm and 2e-2 L2.
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-4), (torch.bfloat16, 2.5e-2)])
 def test_lr_middle(uncond, dtype, tol):
     sd, net = uncond
     dg, _ = oracle_doctree(2, 0)
@@ -72,7 +71,7 @@ def test_lr_middle(uncond, dtype, tol):
     print('ERR lr_middle %s max %.3e l2 %.3e' % (str(dtype), relerr(y, ref), float((y - ref).norm() / ref.norm())))
     assert relerr(y, ref) < tol
     if dtype == torch.bfloat16:
-        assert float((y - ref).norm() / ref.norm()) < 2.5e-2
+        assert float((y - ref).norm() / ref.norm()) < 2e-2
 
 
 @pytest.mark.parametrize('cfg_name', ['uncond', 'cond', 'small'])
@@ -144,7 +143,7 @@ def test_sampler_cuda_graph_matches_eager_and_oracle():
         assert relerr(y.cpu(), x) < 2e-3, (graph, relerr(y.cpu(), x))
     yb = sample_loop(net.unet_hr, net.unet_lr, doc, ddim_steps=steps, noise=noise.to(DEV), act_dtype=torch.bfloat16)
     print('ERR sampler4 bf16 %.3e' % relerr(yb.cpu(), x))
-    assert relerr(yb.cpu(), x) < 4e-2
+    assert relerr(yb.cpu(), x) < 1e-2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -197,7 +196,7 @@ def test_graph_and_config1_against_reference_golden():
 # SURVEY.md 8f-3 ("next" row): the dense LR U-Net as a stand-alone stage-1 denoiser
 # (reference graph_unet_lr.py:184-230, called with unet_type="lr" by octfusion_model_union.py:373)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
 def test_lr_unet_standalone_stage1(uncond, dtype, tol):
     sd, net = uncond
     lr_cfg, _ = R.split_cfg(UNCOND)
