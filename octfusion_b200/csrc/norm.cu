@@ -9,7 +9,6 @@
 //   of_gn_apply     one read + one write      -> y = SiLU(x * scale + shift), concat fused
 // HBM-bound kernels: 16-byte vector accesses, grid sized in multiples of the SM count.
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace of {
 
@@ -58,23 +57,6 @@ template <>
 __device__ __forceinline__ void store_vec<__nv_bfloat16, 1>(__nv_bfloat16* p, const float* f) {
   *p = __float2bfloat16_rn(f[0]);
 }
-
-// raw (unconverted) vector loads: a prefetched bf16x8 vector costs 4 registers instead of 8
-template <typename T, int V> struct RawVec { float f[V]; };
-template <> struct RawVec<__nv_bfloat16, 8> { uint4 q; };
-template <typename T, int V>
-__device__ __forceinline__ void load_raw(const T* p, RawVec<T, V>& r) { load_vec<T, V>(p, r.f); }
-template <>
-__device__ __forceinline__ void load_raw<__nv_bfloat16, 8>(const __nv_bfloat16* p, RawVec<__nv_bfloat16, 8>& r) {
-  r.q = *reinterpret_cast<const uint4*>(p);
-}
-template <typename T, int V>
-__device__ __forceinline__ void raw_to_f(const RawVec<T, V>& r, float* f) {
-#pragma unroll
-  for (int i = 0; i < V; ++i) f[i] = r.f[i];
-}
-template <>
-__device__ __forceinline__ void raw_to_f<__nv_bfloat16, 8>(const RawVec<__nv_bfloat16, 8>& r, float* f) { bf16x8_to_f32(r.q, f); }
 
 struct GnSrc {
   const void* x0; int64_t ld0; int c0;
@@ -248,8 +230,8 @@ template <> struct FastAct<__nv_bfloat16> { static __device__ __forceinline__ fl
 // Each thread owns one channel vector and walks down the rows of its CTA's 256-row chunk; the per-(sample,
 // channel) scale/shift pair stays in registers until the sample id changes.  Chunks that lie inside one sample
 // (nearly all) take the unrolled path: GN_UNROLL loads in flight, no per-row sample lookup.
-template <typename T, int V, int OCC>
-__global__ void __launch_bounds__(256, OCC) gn_apply_kernel(GnSrc s, const float* __restrict__ scale,
+template <typename T, int V>
+__global__ void __launch_bounds__(256, 5) gn_apply_kernel(GnSrc s, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int act, int chunk, int reverse,
                                                           T* y, int64_t ldy) {
   const int C = s.c0 + s.c1;
@@ -258,22 +240,11 @@ __global__ void __launch_bounds__(256, OCC) gn_apply_kernel(GnSrc s, const float
   const int cv = (threadIdx.x % tpr) * V;
   const int64_t r0 = (int64_t)((reverse & 1) ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * chunk;
   const int64_t r1 = min(r0 + (int64_t)chunk, s.rows);
-  const bool active = (int)threadIdx.x < rp * tpr;
-  const T* base = cv < s.c0 ? reinterpret_cast<const T*>(s.x0) + cv : reinterpret_cast<const T*>(s.x1) + (cv - s.c0);
-  const int64_t ld = cv < s.c0 ? s.ld0 : s.ld1;
-  // The first GN_UNROLL rows of this thread are requested BEFORE the sample-id check and the scale/shift loads: a CTA
-  // streams for ~15 us and its dependent prologue loads used to cost 2-3 us of that with nothing in flight.
-  int64_t r = r0 + threadIdx.x / tpr;
-  constexpr int GN_PRE = 2;                                  // (4 spills at the 48-register occupancy target)
-  const bool pre = active && (r + (GN_PRE - 1) * rp < r1);
-  RawVec<T, V> fpre[GN_PRE];
-  if (pre) {
-#pragma unroll
-    for (int u = 0; u < GN_PRE; ++u) load_raw<T, V>(base + (r + u * rp) * ld, fpre[u]);
-  }
   int b0;
   const bool uniform = chunk_is_uniform(s, r0, r1, b0) && !(reverse & 2);
-  if (!active) return;
+  if ((int)threadIdx.x >= rp * tpr) return;
+  const T* base = cv < s.c0 ? reinterpret_cast<const T*>(s.x0) + cv : reinterpret_cast<const T*>(s.x1) + (cv - s.c0);
+  const int64_t ld = cv < s.c0 ? s.ld0 : s.ld1;
   T* yb = y + cv;
   float sc[V], sh[V];
   auto norm_act = [&](float* f) {
@@ -291,19 +262,10 @@ __global__ void __launch_bounds__(256, OCC) gn_apply_kernel(GnSrc s, const float
       for (int i = 0; i < V; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
     }
   };
+  int64_t r = r0 + threadIdx.x / tpr;
   if (uniform) {
 #pragma unroll
     for (int i = 0; i < V; ++i) { sc[i] = scale[(int64_t)b0 * C + cv + i]; sh[i] = shift[(int64_t)b0 * C + cv + i]; }
-    if (pre) {
-#pragma unroll
-      for (int u = 0; u < GN_PRE; ++u) {
-        float f[V];
-        raw_to_f<T, V>(fpre[u], f);
-        norm_act(f);
-        store_vec<T, V>(yb + (r + u * rp) * ldy, f);
-      }
-      r += GN_PRE * rp;
-    }
     for (; r + (GN_UNROLL - 1) * rp < r1; r += GN_UNROLL * rp) {
       float f[GN_UNROLL][V];
 #pragma unroll
@@ -444,15 +406,12 @@ extern "C" int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* 
   if (rows == 0) return OF_OK;
   const int C = c0 + c1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static int occ = -1;                                   // CTAs per SM the kernel is compiled for (OCTFUSION_GN_OCC: 4 | 5)
-  if (occ < 0) { const char* e = getenv("OCTFUSION_GN_OCC"); occ = e ? atoi(e) : 5; }
 #define OF_GN_APPLY_LAUNCH(T, V)                                                              \
   do {                                                                                        \
     OF_REQUIRE(C / V <= 256, "of_gn_apply: C=%d too wide", C);                                \
     const int chunk = gn_chunk_rows(C, (int)sizeof(T));                                       \
     const int grid = (int)((rows + chunk - 1) / chunk);                                       \
-    if (occ == 4) gn_apply_kernel<T, V, 4><<<grid, 256, 0, st>>>(s, scale, shift, act, chunk, reverse, reinterpret_cast<T*>(y), ldy); \
-    else gn_apply_kernel<T, V, 5><<<grid, 256, 0, st>>>(s, scale, shift, act, chunk, reverse, reinterpret_cast<T*>(y), ldy); \
+    gn_apply_kernel<T, V><<<grid, 256, 0, st>>>(s, scale, shift, act, chunk, reverse, reinterpret_cast<T*>(y), ldy); \
   } while (0)
   if (dtype == OF_F32) {
     if (vec_ok(x0, ld0, c0, 4, 4) && vec_ok(x1, ld1, c1, 4, 4) && vec_ok(y, ldy, C, 4, 4)) OF_GN_APPLY_LAUNCH(float, 4);
