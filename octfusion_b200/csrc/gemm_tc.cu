@@ -651,8 +651,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         };
         // two TMEM loads in flight per iteration: the epilogue is latency-bound (tcgen05.ld -> wait -> stores), not
         // issue-bound, and with the MMA warp no longer waiting on barriers a short-K tile leaves it ~8k cycles
+        // The residual row is the one per-row global read of the epilogue; ncu showed its exposed latency (four 16-byte
+        // loads per chunk, L2 / DRAM) as the largest stall of the epilogue warps.  Holding the next chunks' values in
+        // registers spilled (and slowed every layer); instead the 128-byte line of the NEXT chunk pair is prefetched into
+        // L1 (~30 KB are left beside the rings) one iteration ahead -- no registers, one instruction.
+        auto prefetch_res = [&](int c) {
+          if (res != nullptr && n0 + c < g.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(res + n0 + c));
+        };
+        prefetch_res(chalf * 2 * CH);
 #pragma unroll 1
         for (int c0 = chalf * 2 * CH; c0 < BN; c0 += (TC_EPI_WARPS / 4) * 2 * CH) {   // (with 8 warps the quarter's other warp takes the chunks between)
+          prefetch_res(c0 + (TC_EPI_WARPS / 4) * 2 * CH);
           uint32_t accA[32], accB[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)((as * MT + h) * BN + c0);
           const bool pair = c0 + CH < BN;
