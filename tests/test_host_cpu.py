@@ -220,3 +220,28 @@ def test_stat_plan_segment_tables():
         sp = StatPlan(rows_per_sample * batch, batch, rows_per_sample=rows_per_sample, device='cpu')
         cs, ss = brute([r // rows_per_sample for r in range(rows_per_sample * batch)])
         assert sp.chunk_seg.tolist() == cs and sp.n_seg == len(ss)
+
+
+def test_slice_splits_shards_the_batch():
+    """bench.py --gpus N: every rank generates the same B shapes and keeps a contiguous block (strong scaling,
+    BASELINE.json configs[2]).  The blocks partition the label arrays and each block builds the octree of exactly its
+    shapes (per-shape node counts unchanged)."""
+    from octfusion_b200.synth import synth_splits, slice_splits
+    from octfusion_b200 import shard
+    from oracle.octree_util import octree_from_splits
+    b = 6
+    l4, l5 = synth_splits(b, 0)
+    full = octree_from_splits(l4, l5, b)
+    per_shape = lambda oc, d, n: torch.bincount(oc.keys[d] >> 48, minlength=n)            # noqa: E731
+    parts4, parts5, lo_all = [], [], 0
+    for rank in range(4):
+        lo, hi = shard.shard_range(b, rank, 4)
+        assert lo == lo_all
+        lo_all = hi
+        a4, a5 = slice_splits(l4, l5, lo, hi)
+        parts4.append(a4); parts5.append(a5)
+        if hi > lo:
+            oc = octree_from_splits(a4, a5, hi - lo)
+            for d in (5, 6):
+                assert torch.equal(per_shape(oc, d, hi - lo), per_shape(full, d, b)[lo:hi])
+    assert lo_all == b and torch.equal(torch.cat(parts4), l4) and torch.equal(torch.cat(parts5), l5)
