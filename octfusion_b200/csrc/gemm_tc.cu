@@ -310,6 +310,10 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// the same through L1 (experiment: neighbouring taps of one tile gather overlapping row sets)
+__device__ __forceinline__ void cp_async_16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -350,7 +354,7 @@ struct TcCfg {
   // depth of the weight ring.  Its round trip (commit -> MMAs retire -> slot free -> loader wakes -> bulk copy from L2
   // lands -> scout -> MMA warp) is ~2500 cycles, ~3500 for a pair (two more hops): the ring must hold round trip / stage
   // time slots or it paces the whole pipeline (profiles/tc_gather_experiments_r02.md)
-  static constexpr int B_STAGES = UNIFIED ? 0 : CG == 2 ? 6 : (KSUB > 1) ? 2 : (UNI == 2 ? 4 : 3);
+  static constexpr int B_STAGES = UNIFIED ? 0 : CG == 2 ? (UNI == 2 ? 8 : 6) : (KSUB > 1) ? 2 : (UNI == 2 ? 4 : 3);
   static constexpr int A_STAGES = (BUDGET - B_STAGES * B_BYTES) / STAGE_BYTES;
   static constexpr int ACC_COLS = 2 * MT * BN;                      // two accumulator sets (MMA of tile i+1 || epilogue of tile i)
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
@@ -369,7 +373,7 @@ struct TcParams {
   int npad;          // N rounded up to 16 (rows per K block in the packed weight image)
   int m_tiles, n_tiles;   // m_tiles counts CTA tiles of 128*MT rows
   int layout;        // warp-role layout id (tc_roles)
-  int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA, 32 no tap-table reads
+  int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA, 32 no tap-table reads, 64 gather through L1 (cp.async.ca)
   unsigned long long* trace;   // of_tc_trace_set: per-role clock64 stamps of one CTA (diagnostics), or NULL
   int trace_cap, trace_block;
 };
@@ -926,11 +930,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 #pragma unroll
         for (int i = 1; i < TC_BM / 8; ++i) lo = min(lo, t[i]);
         if (!__any_sync(0xffffffffu, lo < -1)) {
+          if (p.debug & 64) {
 #pragma unroll
-          for (int i = 0; i < TC_BM / 8; ++i) {
-            const int32_t tv = t[i];
-            const uint64_t addr = sbase + (uint64_t)(uint32_t)max(tv, 0) * (uint64_t)ldb;
-            cp_async_16(dst0 + i * 1024, reinterpret_cast<const void*>(addr), tv == -1 ? 0u : 16u);
+            for (int i = 0; i < TC_BM / 8; ++i) {
+              const int32_t tv = t[i];
+              const uint64_t addr = sbase + (uint64_t)(uint32_t)max(tv, 0) * (uint64_t)ldb;
+              cp_async_16_ca(dst0 + i * 1024, reinterpret_cast<const void*>(addr), tv == -1 ? 0u : 16u);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < TC_BM / 8; ++i) {
+              const int32_t tv = t[i];
+              const uint64_t addr = sbase + (uint64_t)(uint32_t)max(tv, 0) * (uint64_t)ldb;
+              cp_async_16(dst0 + i * 1024, reinterpret_cast<const void*>(addr), tv == -1 ? 0u : 16u);
+            }
           }
         } else {
 #pragma unroll
@@ -1151,7 +1164,7 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
   const int mt = g_mt, uni = g_uni;
   // widest tile that divides the padded N: fewer re-gathers of A per output column
   if (p.npad % 256 == 0) {
-    if (g_cg == 2 && a.M > 256) return launch_tc<256, 1, 0, 2>(p, st);
+    if (g_cg == 2 && a.M > 256) return uni == 2 ? launch_tc<256, 1, 2, 2>(p, st) : launch_tc<256, 1, 0, 2>(p, st);
     return uni == 1 ? launch_tc<256, 1, 1>(p, st) : uni == 2 ? launch_tc<256, 1, 2>(p, st) : launch_tc<256, 1, 0>(p, st);
   }
   if (p.npad % 128 == 0) {

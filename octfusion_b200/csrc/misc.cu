@@ -200,10 +200,11 @@ __global__ void dense_tap_table_kernel(int mode, int out_bits, int batch, int32_
 __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, int64_t ldx,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            int B, int K, int N, int a_silu, float* __restrict__ out,
-                                                           int64_t ldo) {
+                                                           int64_t ldo, int cols_per_cta) {
+  // One CTA stages the (activated) input rows once and produces cols_per_cta output columns, one per warp at a
+  // time: the staging (32 x K floats) is the expensive part, the weight rows stream through once.
   extern __shared__ float xs[];                     // [min(B,32)][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 8 + warp;
   for (int b0 = 0; b0 < B; b0 += 32) {
     const int nb = min(32, B - b0);
     __syncthreads();
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
       xs[i] = a_silu ? silu_f(v) : v;
     }
     __syncthreads();
-    if (n >= N) continue;
+   for (int n = blockIdx.x * cols_per_cta + warp; n < min(N, (int)(blockIdx.x + 1) * cols_per_cta); n += 8) {
     float acc[32];
 #pragma unroll
     for (int b = 0; b < 32; ++b) acc[b] = 0.0f;
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
       if (lane == b) mine = v;
     }
     if (lane < nb) out[(int64_t)(b0 + lane) * ldo + n] = mine + (bias ? bias[n] : 0.0f);
+   }
   }
 }
 
@@ -267,8 +269,11 @@ extern "C" int of_linear_small(const float* x, int64_t ldx, const float* w_nk, c
     cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cfg = 200 * 1024;
   }
-  linear_small_kernel<<<(N + 7) / 8, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, w_nk, bias, B, K, N,
-                                                                                          a_silu, out, ldo);
+  // about one CTA per SM, columns per CTA a multiple of the 8 warps
+  int cpc = (N + num_sms() - 1) / num_sms();
+  cpc = (cpc + 7) / 8 * 8;
+  linear_small_kernel<<<(N + cpc - 1) / cpc, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, w_nk, bias, B, K, N,
+                                                                                                  a_silu, out, ldo, cpc);
   OF_LAUNCH_CHECK("of_linear_small");
   return OF_OK;
 }

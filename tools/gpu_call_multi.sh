@@ -3,6 +3,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv | head -10
+echo "=== model parity (1 GPU) on this build"; timeout 900 python -m pytest tests/test_gpu_model.py -q -x --timeout 600 2>&1 | tail -2
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 echo "=== unet --gpus $N (strong)"
 timeout 900 $TR --master-port 29501 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_n${N}.json 2> gpurun_out/bench_n${N}.err; tail -2 gpurun_out/bench_n${N}.err
