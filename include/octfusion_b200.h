@@ -53,6 +53,10 @@ int of_tc_trace_set(void* buf, int32_t cap_per_region, int32_t block);
  * roles (scheduling priority follows the warp id).  Defaults: environment OCTFUSION_TC_MT / _UNI / _CG / _LAYOUT, else
  * 2 / 0 / 1 / 0. */
 int of_tc_config(int32_t mt, int32_t uni, int32_t cg, int32_t layout);
+/* how of_gather_gemm_tc fills the gathered operand tiles: 1 = TMA tile::gather4 (one instruction per 4 neighbour rows,
+ * tensor maps built per launch; needs 128-byte aligned rows), 0 = 16-byte cp.async copies by 8 producer warps.  Any other
+ * value keeps the current mode.  Default: environment OCTFUSION_TC_TMAG, else 0. */
+int of_tc_gather_mode(int32_t tma);
 
 /* ------------------------------------------------------------------------------------------
  * Tap-gather GEMM:   out[m, :] = sum_tap  mean_{j in nbr(m, tap)} [ A[j, :] | onehot(type_j) ] . W[tap]

@@ -62,6 +62,7 @@ _PROTOS = {
     'of_abi_sizeof_octree_levels': (C.c_int, []),
     'of_tc_trace_set': (C.c_int, [_vp, _i32, _i32]),
     'of_tc_config': (C.c_int, [_i32, _i32, _i32, _i32]),
+    'of_tc_gather_mode': (C.c_int, [_i32]),
     'of_gather_gemm_simt': (C.c_int, [C.POINTER(GemmArgs), _vp]),
     'of_gather_gemm_tc': (C.c_int, [C.POINTER(GemmArgs), _vp]),
     'of_pack_weight_tc_bytes': (_i64, [_i32, _i32, _i32, _i32]),

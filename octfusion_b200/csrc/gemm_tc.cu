@@ -34,6 +34,7 @@
 // pre-averaged row (of_gather_mean_rows); the weights are re-laid once by of_pack_weight_tc.
 // Measurements behind each of these choices: profiles/tc_gather_experiments_r0*.md.
 #include "common.cuh"
+#include <cuda.h>              // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no -lcuda)
 #include <stdlib.h>
 #include <string.h>
 
@@ -320,6 +321,22 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 __device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// TMA gather (Blackwell tile::gather4): four rows of a 2-D tensor, chosen by four row coordinates, land as four
+// consecutive 128-byte rows of a 128B-swizzled shared-memory tile; a coordinate outside the tensor reads as zeros.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void* map, int col, int r0, int r1, int r2, int r3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+// one row (box 64 x 1) through the same kind of tensor map
+__device__ __forceinline__ void tma_row(uint32_t dst, const void* map, int col, int row, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
@@ -376,6 +393,8 @@ struct TcParams {
   int debug;         // OCTFUSION_TC_DEBUG bit mask (timing experiments only): 1 no gather, 2 no weight copy, 4 no epilogue I/O, 8 no MMA, 32 no tap-table reads, 64 gather through L1 (cp.async.ca)
   unsigned long long* trace;   // of_tc_trace_set: per-role clock64 stamps of one CTA (diagnostics), or NULL
   int trace_cap, trace_block;
+  // TG = 1: tensor maps (bf16, box 64 x 1, 128B swizzle) of a0, a1, the mean rows and the node-type block
+  CUtensorMap tm_a0, tm_a1, tm_multi, tm_nt;
 };
 
 // trace regions (each trace_cap stamps): 0 MMA warp (3 per stage: stage ready, MMAs issued, committed), 1 weight loader (2 per stage:
@@ -407,8 +426,10 @@ __device__ __forceinline__ void warp_reduce_vals(float (&a)[NV], int lane) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN, int MT, int UNI, int CG>
-__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcParams p) {
+// TG = 1: the gathered tiles are filled by the TMA (tile::gather4, one instruction per 4 rows, one warp per 16 KB
+// sub-tile) instead of 16-byte cp.async copies of 8 producer warps.
+template <int BN, int MT, int UNI, int CG, int TG>
+__global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<BN, MT, UNI, CG>;
   constexpr bool U1 = Cfg::UNIFIED;                        // weight tile inside the gather ring's stage
   constexpr int KSUB = Cfg::KSUB, SUBS = Cfg::SUBS;
@@ -444,8 +465,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
 
   if (warp == W.mma && lane == 0) {
     for (int s = 0; s < Cfg::A_STAGES; ++s) {
-      // every producer thread of the stage's sub-tiles (+ the weight loader's expect_tx arrival when the ring is shared)
-      mbar_init(bar_full + 8 * s, SUBS * (TC_PROD_WARPS / TC_GROUPS) * 32 + (U1 ? 1 : 0));
+      // every producer thread of the stage's sub-tiles (TMA gather: one expect_tx arrival per warp = half sub-tile)
+      // (+ the weight loader's expect_tx arrival when the ring is shared)
+      mbar_init(bar_full + 8 * s, (TG ? 2 * SUBS : SUBS * (TC_PROD_WARPS / TC_GROUPS) * 32) + (U1 ? 1 : 0));
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int s = 0; s < Cfg::B_STAGES; ++s) {
@@ -822,7 +844,98 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const TcP
         if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= W.prod0 && warp < W.prod0 + TC_PROD_WARPS) {
+  } else if (TG && warp >= W.prod0 && warp < W.prod0 + TC_PROD_WARPS) {
+    // =========================== gather producers, TMA ===========================
+    // Each of the 4 producer groups (2 warps) owns every 4th 16 KB sub-tile, one warp per 64-row half; lanes 0..15
+    // gather rows 4l..4l+3 of the half with ONE tile::gather4 each (row coordinates = the four tap-table entries,
+    // -1 = no neighbour = outside the tensor = zeros).  A lane whose rows include a multi-neighbour slot (pre-averaged
+    // row of a_multi, another tensor map) issues four single-row copies instead.  The TMA writes the 128B-swizzled rows
+    // and completes the stage's full barrier by bytes: no address arithmetic, no LDGSTS, 1 instruction per 512 bytes.
+    // (A TMA instruction is warp-uniform: the compiler serialises the lanes, ~16 issues per warp and sub-tile.)
+    const int pw = warp - W.prod0;
+    if (lane < 16) {
+      const int grp = pw >> 1;
+      const int rg = (pw & 1) * 16 + lane;                          // 4-row group of the sub-tile, 0..31
+      const int32_t* __restrict__ tab = g.tap_tab;
+      constexpr int KSTEP = TC_GROUPS / MT;
+      const int h = grp % MT;
+      const int my_tiles = (total_tiles - w_first + w_stride - 1) / w_stride;
+      const uint32_t slots = (uint32_t)((p.num_kb + KSUB - 1) / KSUB * SUBS);
+      const uint32_t slot_total = (uint32_t)my_tiles * slots;
+      const int feat_kb = p.cblocks * taps;
+      struct Pos { int ti, s, kb, cb, tap; };
+      auto norm = [&](Pos& c) {
+        while (c.s >= (int)slots) { c.s -= (int)slots; ++c.ti; c.kb = c.s / MT; c.cb = 0; c.tap = c.kb; }
+        while (c.tap >= taps) { c.tap -= taps; ++c.cb; }
+      };
+      auto tile_m0 = [&](int ti) {
+        const int tile = w_first + ti * w_stride;
+        const int ptile = g.reverse ? total_tiles - 1 - tile : tile;
+        return (p.n_tiles == 1 ? ptile : ptile / p.n_tiles) * TILE_ROWS + (h + (int)rank) * TC_BM;
+      };
+      auto fetch_taps = [&](const Pos& c, int32_t* t) {
+        const int m = tile_m0(c.ti) + 4 * rg;
+        if (c.kb >= feat_kb) {                               // node-type block: rows m..m+3 of nt_block
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t[i] = m + i;
+          return;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          t[i] = -1;
+          if (m + i < g.M)
+            t[i] = tab != nullptr ? __ldg(tab + ((uint32_t)(m + i) * (uint32_t)taps + (uint32_t)c.tap))
+                                  : (g.in_rows != nullptr ? __ldg(g.in_rows + m + i) : m + i);
+        }
+      };
+      int32_t tnext[4] = {-1, -1, -1, -1};
+      Pos cur{0, grp, grp / MT, 0, grp / MT};
+      norm(cur);
+      if ((uint32_t)grp < slot_total) fetch_taps(cur, tnext);
+      int tn = 0;
+      for (uint32_t sg_slot = (uint32_t)grp; sg_slot < slot_total; sg_slot += TC_GROUPS) {
+        if (lane == 0) trace_put(p, 2 + grp, tn, tr);
+        const int kb = cur.kb;
+        const int ch = cur.cb * TC_BK;
+        const int32_t t0 = tnext[0], t1 = tnext[1], t2 = tnext[2], t3 = tnext[3];
+        cur.s += TC_GROUPS; cur.kb += KSTEP; cur.tap += KSTEP;
+        norm(cur);
+        if (sg_slot + TC_GROUPS < slot_total) fetch_taps(cur, tnext);
+        const uint32_t sg = sg_slot / SUBS;
+        const uint32_t stage = sg % Cfg::A_STAGES;
+        const uint32_t phase = (sg / Cfg::A_STAGES) & 1u;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (lane == 0) trace_put(p, 2 + grp, tn, tr);
+        const uint32_t bar = bar_full + 8 * stage;
+        const uint32_t dst = stage_base + stage * Cfg::STAGE_BYTES + (sg_slot % SUBS) * Cfg::A_SUB_BYTES + rg * 512;
+        const bool data = kb < p.num_kb && !(p.debug & 1);
+        if (!data) {
+          if (lane == 0) mbar_arrive(bar);
+        } else {
+          if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)Cfg::A_SUB_BYTES / 2);
+          __syncwarp(0xffffu);
+          if (kb >= feat_kb) {
+            tma_gather4(dst, &p.tm_nt, 0, t0, t1, t2, t3, bar);
+          } else {
+            const bool first = ch < g.c0;
+            const void* map = first ? (const void*)&p.tm_a0 : (const void*)&p.tm_a1;
+            const int col = first ? ch : ch - g.c0;
+            if (min(min(t0, t1), min(t2, t3)) >= -1) {
+              tma_gather4(dst, map, col, t0, t1, t2, t3, bar);
+            } else {
+              const int32_t tt[4] = {t0, t1, t2, t3};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (tt[i] < -1) tma_row(dst + i * 128, &p.tm_multi, ch, -2 - tt[i], bar);
+                else tma_row(dst + i * 128, map, col, tt[i], bar);
+              }
+            }
+          }
+        }
+        if (lane == 0) trace_put(p, 2 + grp, tn, tr);
+      }
+    }
+  } else if (!TG && warp >= W.prod0 && warp < W.prod0 + TC_PROD_WARPS) {
     // =========================== gather producers ===========================
     // 4 independent groups of 2 warps; group g produces the 16 KB sub-tiles whose running index is = g mod 4, so 4
     // sub-tiles (64 KB of gathers) are in flight per SM and the memory latency of one is hidden behind the other three.
@@ -1016,10 +1129,45 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int taps, int
 
 
 static int g_mt = -1, g_uni = -1, g_cg = -1, g_layout = -1;   // kernel variant switches (of_tc_config / environment)
+static int g_tg = -1;                                         // 1: TMA gather producers (of_tc_gather_mode / OCTFUSION_TC_TMAG)
+
+// bf16 [rows, cols] tensor with row stride ld (elements) as a TMA tensor map with a 64 x 1 box, 128B swizzle, zero fill
+// outside: the operand of tile::gather4 (and of single-row copies).  cuTensorMapEncodeTiled only encodes -- no device
+// work -- and is fetched from the driver at run time so the library links against cudart only.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_row_map(CUtensorMap* m, const void* base, int64_t cols, int64_t rows, int64_t ld) {
+  static EncodeTiledFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr) {
+      set_error("of_gather_gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+      return OF_E_CUDA;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  if (rows <= 0) rows = 1ll << 30;                      // row count unknown to the caller: only valid rows are ever addressed
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
+  const cuuint32_t box[2] = {64u, 1u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2u, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("of_gather_gemm_tc: cuTensorMapEncodeTiled(cols=%lld rows=%lld ld=%lld) failed: %d", (long long)cols,
+              (long long)rows, (long long)ld, (int)r);
+    return OF_E_CUDA;
+  }
+  return OF_OK;
+}
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cap = 0, g_trace_block = 0;
 
-template <int BN, int MT, int UNI, int CG = 1>
+template <int BN, int MT, int UNI, int CG = 1, int TG = 0>
 static int launch_tc(TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, MT, UNI, CG>;
   // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute of the function
@@ -1027,7 +1175,7 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc_kernel<BN, MT, UNI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc_kernel<BN, MT, UNI, CG, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("of_gather_gemm_tc: cudaFuncSetAttribute(%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -1056,13 +1204,13 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gather_gemm_tc_kernel<BN, MT, UNI, CG>, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gather_gemm_tc_kernel<BN, MT, UNI, CG, TG>, p);
     if (e != cudaSuccess) {
       set_error("of_gather_gemm_tc (pair): launch: %s", cudaGetErrorString(e));
       return OF_E_CUDA;
     }
   } else {
-    gather_gemm_tc_kernel<BN, MT, UNI, CG><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    gather_gemm_tc_kernel<BN, MT, UNI, CG, TG><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
   }
   OF_LAUNCH_CHECK("of_gather_gemm_tc");
   return OF_OK;
@@ -1113,6 +1261,11 @@ extern "C" int of_tc_config(int32_t mt, int32_t uni, int32_t cg, int32_t layout)
   return OF_OK;
 }
 
+extern "C" int of_tc_gather_mode(int32_t tma) {
+  if (tma == 0 || tma == 1) g_tg = tma;
+  return OF_OK;
+}
+
 extern "C" int of_tc_trace_set(void* buf, int32_t cap_per_region, int32_t block) {
   g_trace = reinterpret_cast<unsigned long long*>(buf);
   g_trace_cap = buf ? cap_per_region : 0;
@@ -1145,6 +1298,7 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
   }
   if (a.M == 0) return OF_OK;
   TcParams p;
+  memset(&p.tm_a0, 0, 4 * sizeof(CUtensorMap));
   p.g = a;
   {
     static int dbg = -1;
@@ -1162,6 +1316,22 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
   // OCTFUSION_TC_UNI = 1: weight tile in the gather ring's stage (one barrier pair per stage)
   if (g_mt < 0) { g_mt = env_int("OCTFUSION_TC_MT", 2); g_uni = env_int("OCTFUSION_TC_UNI", 1); g_cg = env_int("OCTFUSION_TC_CG", 1); }
   const int mt = g_mt, uni = g_uni;
+  if (g_tg < 0) g_tg = env_int("OCTFUSION_TC_TMAG", 0);
+  if (g_tg == 1 && a.lda0 % 64 == 0 && (a.c1 == 0 || a.lda1 % 64 == 0) && reinterpret_cast<uintptr_t>(a.a0) % 128 == 0 &&
+      reinterpret_cast<uintptr_t>(a.a1) % 128 == 0 && (a.a_multi == nullptr || a.ld_multi % 64 == 0)) {
+    // TMA gather producers (128-byte aligned rows): tensor maps of the operands
+    if ((rc = make_row_map(&p.tm_a0, a.a0, a.c0, a.rows_a0, a.lda0))) return rc;
+    if (a.c1 > 0) { if ((rc = make_row_map(&p.tm_a1, a.a1, a.c1, a.rows_a1, a.lda1))) return rc; }
+    else p.tm_a1 = p.tm_a0;
+    if (a.a_multi != nullptr) { if ((rc = make_row_map(&p.tm_multi, a.a_multi, a.c0 + a.c1, 0, a.ld_multi))) return rc; }
+    else p.tm_multi = p.tm_a0;
+    if (a.ntype > 0) { if ((rc = make_row_map(&p.tm_nt, a.nt_block, 64, a.M, 64))) return rc; }
+    else p.tm_nt = p.tm_a0;
+    if (p.npad % 256 == 0) return launch_tc<256, 1, 1, 1, 1>(p, st);
+    if (p.npad % 128 == 0) return launch_tc<128, 2, 1, 1, 1>(p, st);
+    if (p.npad % 64 == 0) return launch_tc<64, 2, 0, 1, 1>(p, st);
+    if (p.npad % 32 != 0) return launch_tc<16, 2, 0, 1, 1>(p, st);
+  }
   // widest tile that divides the padded N: fewer re-gathers of A per output column
   if (p.npad % 256 == 0) {
     if (g_cg == 2 && a.M > 256) return uni == 2 ? launch_tc<256, 1, 2, 2>(p, st) : launch_tc<256, 1, 0, 2>(p, st);
