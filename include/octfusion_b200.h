@@ -45,7 +45,7 @@ unsigned long long of_launch_count(void); /* kernels launched by this library so
 int of_abi_sizeof_gemm_args(void);
 int of_abi_sizeof_octree_levels(void);
 /* diagnostics: per-role clock64 stamps of CTA `block` of the following of_gather_gemm_tc launches are written to
- * buf [7][cap_per_region] (uint64); buf = NULL switches tracing off (tools/trace_tc.py decodes the stamps) */
+ * buf [8][cap_per_region] (uint64); buf = NULL switches tracing off (tools/trace_tc.py decodes the stamps) */
 int of_tc_trace_set(void* buf, int32_t cap_per_region, int32_t block);
 /* kernel-variant switches of of_gather_gemm_tc (experiments / tests; a value outside the set keeps the current one):
  * mt in {1, 2}: 128-row tiles per CTA for N <= 128; uni in {0, 1}: weight tile inside the gather ring's stage;

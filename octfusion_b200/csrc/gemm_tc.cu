@@ -397,8 +397,9 @@ struct TcParams {
   CUtensorMap tm_a0, tm_a1, tm_multi, tm_nt;
 };
 
-// trace regions (each trace_cap stamps): 0 MMA warp (3 per stage: stage ready, MMAs issued, committed), 1 weight loader (2 per stage:
-// slot free, issued), 2..5 producer groups (3 per slot: loop top, slot free, issued), 6 epilogue warp 0 (2 per tile)
+// trace regions (each trace_cap stamps): 0 MMA warp (4 per stage: loop top, stage ready, MMAs issued, committed), 1 weight loader (2 per stage:
+// slot free, issued), 2..5 producer groups (3 per slot: loop top, slot free, issued), 6 epilogue warp 0 (2 per tile),
+// 7 scout (1 per stage, indexed by stage: the moment it saw the stage's full barrier complete)
 __device__ __forceinline__ void trace_put(const TcParams& p, int region, int& n, bool on) {
   if (on && n < p.trace_cap) p.trace[(size_t)region * p.trace_cap + n] = (unsigned long long)clock64();
   ++n;
@@ -722,6 +723,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * MT * BN);
       for (int kb = 0; kb < p.num_kb; kb += KSUB) {
+        if (tr && lane == 0) trace_put(p, 0, tn, true);      // (elect.sync picks lane 0 of the converged warp)
         {
           // ready = the slot's fill count has passed the number of fills already consumed (for a pair the leader's scout
           // counts a fill only when the peer has signalled its half as well)
@@ -807,6 +809,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
       bool ok = done < my_total && mbar_test_wait(bar, phase);
       if (CG == 2 && rank == 0 && ok) ok = mbar_test_wait_cluster(pbar, phase);
       if (ok) {
+        if (tr && is_a) {                                  // trace region 7: when the scout saw stage (done * slots + slot) full
+          const uint32_t k = done * nslots + slot;
+          if ((int)k < p.trace_cap) p.trace[(size_t)7 * p.trace_cap + k] = (unsigned long long)clock64();
+        }
         ++done; phase ^= 1u;
         if (CG == 2 && rank != 0) mbar_arrive_cluster(pbar_remote);
         else st_release_cta(flag, done);

@@ -142,6 +142,28 @@ def test_cta_pair_equals_single_cta_bitwise(pair_variant):
     assert torch.equal(a, b) and torch.equal(a._of_stats.part, b._of_stats.part)
 
 
+@pytest.fixture
+def tma_gather():
+    """fill the gathered operand tiles with the TMA (cp.async.bulk.tensor tile::gather4) for the duration of a test"""
+    from octfusion_b200._lib import lib
+    lib.of_tc_gather_mode(1)
+    yield
+    lib.of_tc_gather_mode(0)
+
+
+@pytest.mark.parametrize('d,cin,cout,nt', [(4, 256, 512, 3), (6, 128, 128, 5), (6, 64, 8, 5), (5, 768, 64, 4)])
+def test_graphconv_bf16_tma_gather_equals_cp_async_bitwise(tma_gather, d, cin, cout, nt):
+    """tile::gather4 producers: a missing neighbour is a row coordinate outside the tensor (zero fill), multi-neighbour
+    slots come from the mean-row tensor map, the node-type block from its own map -- same bytes in shared memory as the
+    cp.async producers, hence the same result bit for bit"""
+    from octfusion_b200._lib import lib
+    y, ref32, refbf = _graphconv_case(2, d, cin, cout, nt, torch.bfloat16)
+    lib.of_tc_gather_mode(0)
+    y0, _, _ = _graphconv_case(2, d, cin, cout, nt, torch.bfloat16)
+    assert relerr(y, refbf) < 8e-3
+    assert torch.equal(y, y0)
+
+
 # ------------------------------------------------------------------------------------------------
 # plain GEMMs with the fused epilogues
 # ------------------------------------------------------------------------------------------------

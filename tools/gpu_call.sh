@@ -1,5 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-timeout 2300 tools/exp_tmag.sh > gpurun_out/exp_tmag_18.log 2>&1
-tail -n 150 gpurun_out/exp_tmag_18.log
+export PYTHONUNBUFFERED=1
+{
+echo "##### DEBUG=7"; OCTFUSION_TC_DEBUG=7 python tools/trace_tc.py "6,128,128;4,512,512" 2>&1 | grep -E "==|stage period|stage ready|commit ->|loop top|issue MMAs|commits"
+echo "##### DEBUG=15 (no MMA either)"; OCTFUSION_TC_DEBUG=15 python tools/trace_tc.py "6,128,128;4,512,512" 2>&1 | grep -E "==|stage period|stage ready|commit ->|loop top|issue MMAs|commits"
+echo "##### plain"; python tools/trace_tc.py "6,128,128;4,512,512" 2>&1 | grep -E "==|stage period|stage ready|commit ->|loop top|issue MMAs|commits"
+} > gpurun_out/trace_23.log 2>&1
+cat gpurun_out/trace_23.log
