@@ -92,7 +92,9 @@ class HRStepper:
         if self.graph is None:
             # eager warm-up on a side copy of the state (builds packed weights, tables, func attributes)
             keep = self.x.clone()
-            c0 = _lib.launch_count()
+            self._body()
+            self.set_latent(keep)
+            c0 = _lib.launch_count()             # second pass: the steady-state launches only (no weight packing)
             self._body()
             self.kernels_per_step = _lib.launch_count() - c0
             self.set_latent(keep)
