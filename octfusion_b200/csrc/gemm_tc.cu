@@ -22,6 +22,7 @@
 //               tap table -> sixteen 16-byte cp.async (LDGSTS) per thread straight into the swizzled A stage,
 //               completion by cp.async.mbarrier.arrive.noinc; no registers, no waiting.  The producers' address
 //               arithmetic is kept to 4 instructions per copy (it shares issue slots with the MMA warp).
+//               Opt-in alternative (TG = 1): the TMA gathers the rows, cp.async.bulk.tensor tile::gather4 (measured slower).
 // A CTA tile is MT (1 or 2) row tiles of 128 rows x BN columns; with MT = 2 (BN <= 128) one streamed weight tile
 // feeds both row tiles.  Pipelines: shared-memory ring(s) with full/empty mbarriers between {producers, loader} and
 // the MMA warp; two sets of TMEM accumulators (full/empty mbarriers) between MMA and epilogue, so tile i+1 is computed

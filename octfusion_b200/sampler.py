@@ -45,6 +45,7 @@ class HRStepper:
         self._graph_key = None
         self.use_cuda_graph = use_cuda_graph
         self.kernels_per_step = 0
+        self._pipe = None
 
     def _weights_key(self):
         """fingerprint of every parameter of the two nets: the captured graph bakes in device copies of the weights
@@ -64,6 +65,48 @@ class HRStepper:
         self.x.copy_(x)
         if self.x_act is not None:
             ops.copy_rows(self.x, self.x_act, self.x.shape[0], self.x.shape[1])
+
+    # ---- latents that live in (pinned) host memory: one step per call, copies overlapped with the previous / next step ----
+    def step_host(self, x_host, log_snr: float, log_snr_next: float, out_host):
+        """One denoising step of a latent in pinned host memory: x_host -> device, step, result -> out_host.
+
+        Asynchronous and double-buffered: the host->device copy of THIS call runs on a copy stream while the previous
+        call's step is still computing, and the device->host copy of this call's result runs on a second copy stream
+        while the next call computes (PCIe is full duplex).  Independent latents only -- a call does not see the
+        previous call's output.  Call sync_host() before reading out_host."""
+        cur = torch.cuda.current_stream()
+        if self._pipe is None:
+            mk = lambda: torch.empty_like(self.x)                       # noqa: E731
+            ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]       # noqa: E731
+            self._pipe = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(), xin=[mk(), mk()], out=[mk(), mk()],
+                              loaded=ev(), consumed=ev(), produced=ev(), drained=ev(), n=0)
+        q = self._pipe
+        i, s = q['n'], q['n'] & 1
+        with torch.cuda.stream(q['h2d']):
+            if i >= 2:
+                q['h2d'].wait_event(q['consumed'][s])                   # step i-2 has read this staging buffer
+            q['xin'][s].copy_(x_host, non_blocking=True)
+            q['loaded'][s].record(q['h2d'])
+        cur.wait_event(q['loaded'][s])
+        self.set_latent(q['xin'][s])
+        q['consumed'][s].record(cur)
+        self.step(log_snr, log_snr_next)
+        if i >= 2:
+            cur.wait_event(q['drained'][s])                             # the result of step i-2 has left this buffer
+        q['out'][s].copy_(self.x)
+        q['produced'][s].record(cur)
+        with torch.cuda.stream(q['d2h']):
+            q['d2h'].wait_event(q['produced'][s])
+            out_host.copy_(q['out'][s], non_blocking=True)
+            q['drained'][s].record(q['d2h'])
+        q['n'] = i + 1
+
+    def sync_host(self):
+        """make the current stream wait for every outstanding result copy of step_host()"""
+        if self._pipe is not None:
+            cur = torch.cuda.current_stream()
+            for k in range(min(2, self._pipe['n'])):
+                cur.wait_event(self._pipe['drained'][k])
 
     def forward_eps(self):
         xin = self.x if self.x_act is None else self.x_act
