@@ -1339,6 +1339,40 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
     if (p.npad % 64 == 0) return launch_tc<64, 2, 0, 1, 1>(p, st);
     if (p.npad % 32 != 0) return launch_tc<16, 2, 0, 1, 1>(p, st);
   }
+  // Small M (the dense 4^3 / 8^3 levels: 2048 / 16384 rows): the widest tile would leave most SMs idle (16 row tiles of 128
+  // rows for 148 SMs) with every CTA walking the whole K loop alone.  Take the widest tile shape whose tile count still
+  // fills 3/4 of the SMs, else the shape with the most tiles: narrower column tiles re-gather the (L2-resident) rows but
+  // split the weight stream and the MMAs over more SMs.  The statistics granule follows N, so a fused-statistics launch
+  // only moves between shapes with the same granule.
+  if (g_cg != 2 && mt == 2 && p.npad % 32 == 0) {
+    struct Shape { int bn, mt; };
+    static const Shape shapes[] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}, {32, 2}, {32, 1}};
+    auto tiles = [&](const Shape& sh) { return (int64_t)((a.M + 128 * sh.mt - 1) / (128 * sh.mt)) * (p.npad / sh.bn); };
+    const bool wide_gran = p.npad % 128 == 0;
+    int best = -1;
+    int64_t best_tiles = -1;
+    const int64_t enough = (int64_t)num_sms() * 3 / 4;
+    for (int i = 0; i < 7; ++i) {
+      const Shape& sh = shapes[i];
+      if (p.npad % sh.bn != 0) continue;
+      if (a.stat_out != nullptr && (sh.bn >= 128) != wide_gran) continue;
+      const int64_t t = tiles(sh);
+      if (best < 0) { best = i; best_tiles = t; }            // the default: the widest shape that divides N
+      if (best_tiles >= enough) break;
+      if (t > best_tiles) { best = i; best_tiles = t; }
+      if (t >= enough) break;
+    }
+    if (best >= 2) {                                         // (0, 1 = the defaults handled below)
+      switch (best) {
+        case 2: return launch_tc<128, 1, 0>(p, st);
+        case 3: return launch_tc<64, 2, 0>(p, st);
+        case 4: return launch_tc<64, 1, 0>(p, st);
+        case 5: return launch_tc<32, 2, 0>(p, st);
+        default: return launch_tc<32, 1, 0>(p, st);
+      }
+    }
+    if (best == 1 && p.npad % 256 == 0) return uni == 1 ? launch_tc<128, 2, 1>(p, st) : launch_tc<128, 2, 0>(p, st);
+  }
   // widest tile that divides the padded N: fewer re-gathers of A per output column
   if (p.npad % 256 == 0) {
     if (g_cg == 2 && a.M > 256) return uni == 2 ? launch_tc<256, 1, 2, 2>(p, st) : launch_tc<256, 1, 0, 2>(p, st);

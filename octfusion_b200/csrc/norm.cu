@@ -409,7 +409,15 @@ extern "C" int of_gn_apply(const void* x0, int64_t ld0, int32_t c0, const void* 
 #define OF_GN_APPLY_LAUNCH(T, V)                                                              \
   do {                                                                                        \
     OF_REQUIRE(C / V <= 256, "of_gn_apply: C=%d too wide", C);                                \
-    const int chunk = gn_chunk_rows(C, (int)sizeof(T));                                       \
+    int chunk = gn_chunk_rows(C, (int)sizeof(T));                                             \
+    {                                                                                         \
+      /* small tensors (the dense 4^3 / 8^3 levels: 2048 / 16384 rows): rather 4 CTAs per SM with one or two     \
+         passes each than a handful of CTAs walking 256 rows -- those launches were latency-bound at 30 us */   \
+      const int rp = 256 / (C / V);                                                           \
+      int64_t want = (rows + 4 * num_sms() - 1) / (4 * num_sms());                            \
+      want = (want + rp - 1) / rp * rp;                                                       \
+      if (want < chunk) chunk = (int)want;                                                    \
+    }                                                                                         \
     const int grid = (int)((rows + chunk - 1) / chunk);                                       \
     gn_apply_kernel<T, V><<<grid, 256, 0, st>>>(s, scale, shift, act, chunk, reverse, reinterpret_cast<T*>(y), ldy); \
   } while (0)
