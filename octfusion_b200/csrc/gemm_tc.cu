@@ -38,6 +38,7 @@
 #include <cuda.h>              // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no -lcuda)
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 namespace of {
 
@@ -643,9 +644,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
           }
           if constexpr (CH == 32) {
             if (nseg > 0 && full) {
-              // (sum, sum of squares) of every GRAN-channel granule of my row; rows beyond M contribute zero.
-              // GRAN = 4 for the wide layers, 2 for N < 128 (a 64-channel norm has 2 channels per group).
-              constexpr int GRAN = BN >= 128 ? 4 : 2;
+             // (sum, sum of squares) of every GRAN-channel granule of my row; rows beyond M contribute zero.
+             // GRAN = 4 when N is a multiple of 128, else 2 (a 64-channel norm has 2 channels per group) -- a property of
+             // the layer, not of the tile shape, so that the small-M dispatch may run a wide layer on narrow tiles.
+             auto stats = [&](auto gran_c) {
+              constexpr int GRAN = decltype(gran_c)::value;
               constexpr int NV = 2 * 32 / GRAN;
               float a[NV];
 #pragma unroll
@@ -674,6 +677,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
                   if (writer) dst[(int64_t)slot * nval] = t[0];
                 }
               }
+             };
+             if (g.N % 128 == 0) stats(std::integral_constant<int, 4>{});
+             else stats(std::integral_constant<int, 2>{});
             }
           }
         };
@@ -1342,20 +1348,17 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
   // Small M (the dense 4^3 / 8^3 levels: 2048 / 16384 rows): the widest tile would leave most SMs idle (16 row tiles of 128
   // rows for 148 SMs) with every CTA walking the whole K loop alone.  Take the widest tile shape whose tile count still
   // fills 3/4 of the SMs, else the shape with the most tiles: narrower column tiles re-gather the (L2-resident) rows but
-  // split the weight stream and the MMAs over more SMs.  The statistics granule follows N, so a fused-statistics launch
-  // only moves between shapes with the same granule.
+  // split the weight stream and the MMAs over more SMs.  (The statistics granule follows N, not the tile shape.)
   if (g_cg != 2 && mt == 2 && p.npad % 32 == 0) {
     struct Shape { int bn, mt; };
     static const Shape shapes[] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}, {32, 2}, {32, 1}};
     auto tiles = [&](const Shape& sh) { return (int64_t)((a.M + 128 * sh.mt - 1) / (128 * sh.mt)) * (p.npad / sh.bn); };
-    const bool wide_gran = p.npad % 128 == 0;
     int best = -1;
     int64_t best_tiles = -1;
     const int64_t enough = (int64_t)num_sms() * 3 / 4;
     for (int i = 0; i < 7; ++i) {
       const Shape& sh = shapes[i];
       if (p.npad % sh.bn != 0) continue;
-      if (a.stat_out != nullptr && (sh.bn >= 128) != wide_gran) continue;
       const int64_t t = tiles(sh);
       if (best < 0) { best = i; best_tiles = t; }            // the default: the widest shape that divides N
       if (best_tiles >= enough) break;

@@ -312,10 +312,8 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
     g.dtype = dt(a0)
     st_obj = None
     g.stat_out, g.stat_chunk_seg, g.stat_seg_slot, g.stat_sample, g.stat_rows_per_sample = None, None, None, None, 0
-    # (tensors of a few thousand rows -- the dense 4^3 level -- keep the stand-alone statistics kernel: their GEMM then
-    # is free to use narrow column tiles that fill the SMs, of_gather_gemm_tc's small-M dispatch)
     if (stats is not None and _FUSE_STATS and use_tc and n % 32 == 0 and out_rows is None and stats.rows == m
-            and not g.out_f32 and m > 4096):
+            and not g.out_f32):
         st_obj = Stats(stats.new_part(n, tc_stat_gran(n)), stats, n, tc_stat_gran(n))
         g.stat_out, g.stat_chunk_seg = st_obj.part.data_ptr(), stats.chunk_seg.data_ptr()
         g.stat_seg_slot = stats.seg_slot.data_ptr()
