@@ -48,10 +48,11 @@ int of_abi_sizeof_octree_levels(void);
  * buf [8][cap_per_region] (uint64); buf = NULL switches tracing off (tools/trace_tc.py decodes the stamps) */
 int of_tc_trace_set(void* buf, int32_t cap_per_region, int32_t block);
 /* kernel-variant switches of of_gather_gemm_tc (experiments / tests; a value outside the set keeps the current one):
- * mt in {1, 2}: 128-row tiles per CTA for N <= 128; uni in {0, 1}: weight tile inside the gather ring's stage;
+ * mt in {1, 2}: 128-row tiles per CTA for N <= 128; uni in {0, 1, 2}: 1 = weight tile inside the gather ring's stage, 2 = deeper separate weight ring;
  * cg in {1, 2}: 2 = CTA pairs (tcgen05 cta_group::2) for the 256-wide tiles; layout in {0, 1}: order of the warp
  * roles (scheduling priority follows the warp id).  Defaults: environment OCTFUSION_TC_MT / _UNI / _CG / _LAYOUT, else
- * 2 / 0 / 1 / 0. */
+ * 2 / 1 / 1 / 0.  Small M (fewer 128-row tiles than SMs) overrides the tile shape: the widest shape that still fills the
+ * SMs (gemm_tc.cu, of_gather_gemm_tc). */
 int of_tc_config(int32_t mt, int32_t uni, int32_t cg, int32_t layout);
 /* how of_gather_gemm_tc fills the gathered operand tiles: 1 = TMA tile::gather4 (one instruction per 4 neighbour rows,
  * tensor maps built per launch; needs 128-byte aligned rows), 0 = 16-byte cp.async copies by 8 producer warps.  Any other
