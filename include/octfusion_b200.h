@@ -140,6 +140,14 @@ int of_gather_gemm_simt(const of_gemm_args* args, void* stream);
 /* tcgen05 / TMEM path (bf16 operands, fp32 accumulate). Requires dtype = OF_BF16,
  * (c0 % 64 == 0), (c1 % 64 == 0), N % 16 == 0 and w packed by of_pack_weight_tc. */
 int of_gather_gemm_tc(const of_gemm_args* args, void* stream);
+/* Split-K variant for launches whose row tiles cannot fill the GPU (the dense 4^3 / 8^3 levels: M = 2048 at B = 32, with
+ * K up to 13824): of_tc_splitk_plan returns the number S of K ranges this library would use for `args` (1 = do not
+ * split).  With S > 1 the caller provides a workspace of S * M * N floats and calls of_gather_gemm_tc_splitk: pass 1
+ * runs the same tcgen05 kernel over (output tile, K range) pairs writing fp32 partial sums, pass 2 adds the ranges in
+ * order (bit-reproducible) with bias / row_add / resid, stores `out` and computes the stat_out statistics.  Same
+ * arguments and results as of_gather_gemm_tc up to fp32 summation order. */
+int of_tc_splitk_plan(const of_gemm_args* args);
+int of_gather_gemm_tc_splitk(const of_gemm_args* args, int32_t splits, float* workspace, void* stream);
 /* size in bytes of the packed image for K_feat = taps*(c0+c1) feature rows + ntype one-hot rows */
 int64_t of_pack_weight_tc_bytes(int32_t taps, int32_t c, int32_t ntype, int32_t N);
 /* w_canonical: fp32 [taps*(c+ntype), N]; out: packed bf16 image */

@@ -65,6 +65,8 @@ _PROTOS = {
     'of_tc_gather_mode': (C.c_int, [_i32]),
     'of_gather_gemm_simt': (C.c_int, [C.POINTER(GemmArgs), _vp]),
     'of_gather_gemm_tc': (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    'of_tc_splitk_plan': (C.c_int, [C.POINTER(GemmArgs)]),
+    'of_gather_gemm_tc_splitk': (C.c_int, [C.POINTER(GemmArgs), _i32, _vp, _vp]),
     'of_pack_weight_tc_bytes': (_i64, [_i32, _i32, _i32, _i32]),
     'of_pack_weight_tc': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'of_repack_weight': (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),

@@ -387,7 +387,9 @@ struct TcCfg {
 
 struct TcParams {
   of_gemm_args g;
-  int num_kb;        // K blocks per tile
+  int num_kb;        // K blocks per (virtual) tile = all K blocks / ksplit
+  int ksplit;        // split-K: every output tile is computed as ksplit virtual tiles over consecutive K ranges, each
+                     // writing fp32 partial sums to its own [M, N] slab of the workspace (of_gather_gemm_tc_splitk)
   int cblocks;       // (c0+c1)/64
   int npad;          // N rounded up to 16 (rows per K block in the packed weight image)
   int m_tiles, n_tiles;   // m_tiles counts CTA tiles of 128*MT rows
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
   const of_gemm_args& g = p.g;
   const int taps = g.taps;
   // work items: CTA tiles of 128*MT rows (CG = 1) or pair tiles of 256 rows that both CTAs of a pair walk together
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;   // virtual tile v: output tile v / ksplit, K range v % ksplit
   uint32_t rank = 0;
   if constexpr (CG == 2) rank = cluster_ctarank();
   const int w_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -505,7 +507,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     const int r = qw * 32 + lane;
     int it = 0, tn = 0;
     for (int tile = w_first; tile < total_tiles; tile += w_stride, ++it) {
-      const int ptile = g.reverse ? total_tiles - 1 - tile : tile;
+      const int vtile = g.reverse ? total_tiles - 1 - tile : tile;
+      const int ptile = vtile / p.ksplit;
+      const int64_t split_row0 = (int64_t)(vtile - ptile * p.ksplit) * g.M;        // this K range's slab of the workspace
       const int mt0 = (ptile / p.n_tiles) * TILE_ROWS + (int)rank * TC_BM, n0 = (ptile % p.n_tiles) * BN;
       const int as = it & 1;
       mbar_wait_relaxed(bar_tfull + 8 * as, (it >> 1) & 1);
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
       for (int h = 0; h < MT; ++h) {
         const int m = mt0 + h * TC_BM + r;
         const bool row_ok = m < g.M;
-        const int64_t orow = row_ok ? (g.out_rows ? (int64_t)g.out_rows[m] : (int64_t)m) : 0;
+        const int64_t orow = row_ok ? (g.out_rows ? (int64_t)g.out_rows[m] : (int64_t)m + split_row0) : 0;
         const float* radd = (row_ok && g.row_add) ? g.row_add + (int64_t)g.row_add_idx[m] * g.ld_row_add : nullptr;
         const __nv_bfloat16* res =
             (row_ok && g.resid) ? reinterpret_cast<const __nv_bfloat16*>(g.resid) + (int64_t)m * g.ld_resid : nullptr;
@@ -837,7 +841,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     const uint8_t* wp = reinterpret_cast<const uint8_t*>(g.w);
     for (int tile = w_first; tile < total_tiles; tile += w_stride) {
       // a CTA of a pair streams its half of the tile's weight rows
-      const int n0 = ((g.reverse ? total_tiles - 1 - tile : tile) % p.n_tiles) * BN + (int)rank * (BN / CG);
+      const int vtile = g.reverse ? total_tiles - 1 - tile : tile;
+      const int n0 = ((vtile / p.ksplit) % p.n_tiles) * BN + (int)rank * (BN / CG);
+      const int kb_off = (vtile % p.ksplit) * p.num_kb;            // first K block of this virtual tile's range
       for (int kb = 0; kb < p.num_kb; kb += KSUB) {
         const uint32_t bfull = U1 ? bar_full + 8 * stage : bar_bfull + 8 * stage;
         mbar_wait((U1 ? bar_empty : bar_bempty) + 8 * stage, phase ^ 1);
@@ -849,7 +855,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
             const int nk = min(KSUB, p.num_kb - kb);
             mbar_arrive_expect_tx(bfull, (uint32_t)nk * Cfg::B_SUB_BYTES);
             for (int j = 0; j < nk; ++j)
-              bulk_g2s(b_addr + j * Cfg::B_SUB_BYTES, wp + ((int64_t)(kb + j) * p.npad + n0) * 128, Cfg::B_SUB_BYTES, bfull);
+              bulk_g2s(b_addr + j * Cfg::B_SUB_BYTES, wp + ((int64_t)(kb_off + kb + j) * p.npad + n0) * 128, Cfg::B_SUB_BYTES, bfull);
           }
         }
         __syncwarp();
@@ -875,20 +881,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
       const int my_tiles = (total_tiles - w_first + w_stride - 1) / w_stride;
       const uint32_t slots = (uint32_t)((p.num_kb + KSUB - 1) / KSUB * SUBS);
       const uint32_t slot_total = (uint32_t)my_tiles * slots;
-      const int feat_kb = p.cblocks * taps;
       struct Pos { int ti, s, kb, cb, tap; };
+      auto vtile_of = [&](int ti) { const int tile = w_first + ti * w_stride; return g.reverse ? total_tiles - 1 - tile : tile; };
+      auto kb_off = [&](int ti) { return (vtile_of(ti) % p.ksplit) * p.num_kb; };
       auto norm = [&](Pos& c) {
-        while (c.s >= (int)slots) { c.s -= (int)slots; ++c.ti; c.kb = c.s / MT; c.cb = 0; c.tap = c.kb; }
+        while (c.s >= (int)slots) { c.s -= (int)slots; ++c.ti; c.kb = c.s / MT; c.cb = 0; c.tap = kb_off(c.ti) + c.kb; }
         while (c.tap >= taps) { c.tap -= taps; ++c.cb; }
       };
       auto tile_m0 = [&](int ti) {
-        const int tile = w_first + ti * w_stride;
-        const int ptile = g.reverse ? total_tiles - 1 - tile : tile;
+        const int ptile = vtile_of(ti) / p.ksplit;
         return (p.n_tiles == 1 ? ptile : ptile / p.n_tiles) * TILE_ROWS + (h + (int)rank) * TC_BM;
       };
       auto fetch_taps = [&](const Pos& c, int32_t* t) {
         const int m = tile_m0(c.ti) + 4 * rg;
-        if (c.kb >= feat_kb) {                               // node-type block: rows m..m+3 of nt_block
+        if (c.cb >= p.cblocks) {                             // node-type block: rows m..m+3 of nt_block
 #pragma unroll
           for (int i = 0; i < 4; ++i) t[i] = m + i;
           return;
@@ -902,13 +908,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
         }
       };
       int32_t tnext[4] = {-1, -1, -1, -1};
-      Pos cur{0, grp, grp / MT, 0, grp / MT};
+      Pos cur{0, grp, grp / MT, 0, kb_off(0) + grp / MT};
       norm(cur);
       if ((uint32_t)grp < slot_total) fetch_taps(cur, tnext);
       int tn = 0;
       for (uint32_t sg_slot = (uint32_t)grp; sg_slot < slot_total; sg_slot += TC_GROUPS) {
         if (lane == 0) trace_put(p, 2 + grp, tn, tr);
         const int kb = cur.kb;
+        const int cur_cb = cur.cb;
         const int ch = cur.cb * TC_BK;
         const int32_t t0 = tnext[0], t1 = tnext[1], t2 = tnext[2], t3 = tnext[3];
         cur.s += TC_GROUPS; cur.kb += KSTEP; cur.tap += KSTEP;
@@ -927,7 +934,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
         } else {
           if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)Cfg::A_SUB_BYTES / 2);
           __syncwarp(0xffffu);
-          if (kb >= feat_kb) {
+          if (cur_cb >= p.cblocks) {
             tma_gather4(dst, &p.tm_nt, 0, t0, t1, t2, t3, bar);
           } else {
             const bool first = ch < g.c0;
@@ -971,21 +978,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     const int my_tiles = (total_tiles - w_first + w_stride - 1) / w_stride;
     const uint32_t slots = (uint32_t)((p.num_kb + KSUB - 1) / KSUB * SUBS);
     const uint32_t slot_total = (uint32_t)my_tiles * slots;
-    const int feat_kb = p.cblocks * taps;
     // position of a slot inside this CTA's work: (tile iteration, slot, K block, channel block, tap), advanced
     // incrementally -- no integer divisions in the producer loop (its instruction stream competes with the MMA warp)
     struct Pos { int ti, s, kb, cb, tap; };
+    auto vtile_of = [&](int ti) { const int tile = w_first + ti * w_stride; return g.reverse ? total_tiles - 1 - tile : tile; };
+    auto kb_off = [&](int ti) { return (vtile_of(ti) % p.ksplit) * p.num_kb; };
     auto norm = [&](Pos& c) {
-      while (c.s >= (int)slots) { c.s -= (int)slots; ++c.ti; c.kb = c.s / MT; c.cb = 0; c.tap = c.kb; }
+      // (cb, tap) = the ABSOLUTE K block kb_off + kb of the tile's K range (split-K), kb stays relative to the range
+      while (c.s >= (int)slots) { c.s -= (int)slots; ++c.ti; c.kb = c.s / MT; c.cb = 0; c.tap = kb_off(c.ti) + c.kb; }
       while (c.tap >= taps) { c.tap -= taps; ++c.cb; }
     };
     auto tile_m0 = [&](int ti) {
-      const int tile = w_first + ti * w_stride;
-      const int ptile = g.reverse ? total_tiles - 1 - tile : tile;
+      const int ptile = vtile_of(ti) / p.ksplit;
       return (p.n_tiles == 1 ? ptile : ptile / p.n_tiles) * TILE_ROWS + (h + (int)rank) * TC_BM;
     };
     auto fetch_taps = [&](const Pos& c, int32_t* t) {
-      if (c.kb >= feat_kb || (p.debug & 32)) return;
+      if (c.cb >= p.cblocks || (p.debug & 32)) return;          // (the node-type block: cb == cblocks)
       const int m0 = tile_m0(c.ti);
       if (tab != nullptr) {
         const uint32_t base = (uint32_t)(m0 + rbase) * (uint32_t)taps + (uint32_t)c.tap;     // < 2^31 (checked on host)
@@ -1013,7 +1021,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     int32_t tnext[TC_BM / 8];
 #pragma unroll
     for (int i = 0; i < TC_BM / 8; ++i) tnext[i] = -1;
-    Pos cur{0, grp, grp / MT, 0, grp / MT};
+    Pos cur{0, grp, grp / MT, 0, kb_off(0) + grp / MT};
     norm(cur);
     if ((uint32_t)grp < slot_total) fetch_taps(cur, tnext);
     int tn = 0;
@@ -1036,7 +1044,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
       const uint32_t a_addr = stage_base + stage * Cfg::STAGE_BYTES + (sg_slot % SUBS) * Cfg::A_SUB_BYTES;
       const bool data = kb < p.num_kb && !(p.debug & 1);
       if (!data) {
-      } else if (kb < feat_kb) {
+      } else if (cur_cb < p.cblocks) {
         const int ch = cur_cb * TC_BK;
         const __nv_bfloat16* src;
         int64_t ld;
@@ -1198,7 +1206,7 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
   }
   p.m_tiles = (p.g.M + TC_BM * MT * CG - 1) / (TC_BM * MT * CG);
   p.n_tiles = p.npad / BN;
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles * p.ksplit;
   int grid = CG * total < num_sms() ? CG * total : (num_sms() / CG) * CG;
   {
     static int lim = -1;                                   // OCTFUSION_TC_GRID: cap the CTA count (experiments)
@@ -1286,7 +1294,9 @@ extern "C" int of_tc_trace_set(void* buf, int32_t cap_per_region, int32_t block)
   return OF_OK;
 }
 
-extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
+// ksplit > 1 (of_gather_gemm_tc_splitk): K is cut into ksplit equal ranges of whole K blocks, the virtual tile (output
+// tile, range) writes its fp32 partial sums into slab `range` of args->out ([ksplit][M][N] fp32, no epilogue extras)
+static int run_tc(const of_gemm_args* args, int ksplit, void* stream) {
   int rc = check_gemm_args(args, "of_gather_gemm_tc");
   if (rc) return rc;
   const of_gemm_args& a = *args;
@@ -1323,12 +1333,25 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
   p.layout = g_layout;
   p.cblocks = (a.c0 + a.c1) / 64;
   p.num_kb = p.cblocks * a.taps + (a.ntype > 0 ? 1 : 0);
+  p.ksplit = 1;
   p.npad = (a.N + 15) / 16 * 16;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // experiment switches (tools/exp_tc.sh): OCTFUSION_TC_MT = row tiles per CTA for the narrow layers (1 | 2),
   // OCTFUSION_TC_UNI = 1: weight tile in the gather ring's stage (one barrier pair per stage)
   if (g_mt < 0) { g_mt = env_int("OCTFUSION_TC_MT", 2); g_uni = env_int("OCTFUSION_TC_UNI", 1); g_cg = env_int("OCTFUSION_TC_CG", 1); }
   const int mt = g_mt, uni = g_uni;
+  if (ksplit > 1) {
+    OF_REQUIRE(p.num_kb % ksplit == 0 && p.npad % 32 == 0 && a.N == p.npad && a.out_rows == nullptr && a.out_f32 == 1 &&
+                   a.bias == nullptr && a.row_add == nullptr && a.resid == nullptr && a.stat_out == nullptr,
+               "of_gather_gemm_tc_splitk: internal argument error");
+    p.ksplit = ksplit;
+    p.num_kb /= ksplit;
+    // one 128-row tile per CTA: the point is many short K loops
+    if (p.npad % 256 == 0) return uni == 1 ? launch_tc<256, 1, 1>(p, st) : launch_tc<256, 1, 0>(p, st);
+    if (p.npad % 128 == 0) return launch_tc<128, 1, 0>(p, st);
+    if (p.npad % 64 == 0) return launch_tc<64, 1, 0>(p, st);
+    return launch_tc<32, 1, 0>(p, st);
+  }
   if (g_tg < 0) g_tg = env_int("OCTFUSION_TC_TMAG", 0);
   if (g_tg == 1 && a.lda0 % 64 == 0 && (a.c1 == 0 || a.lda1 % 64 == 0) && reinterpret_cast<uintptr_t>(a.a0) % 128 == 0 &&
       reinterpret_cast<uintptr_t>(a.a1) % 128 == 0 && (a.a_multi == nullptr || a.ld_multi % 64 == 0)) {
@@ -1388,4 +1411,125 @@ extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) {
   if (p.npad % 64 == 0) return launch_tc<64, 2, 0>(p, st);
   if (p.npad % 32 == 0) return launch_tc<32, 2, 0>(p, st);
   return launch_tc<16, 2, 0>(p, st);
+}
+
+extern "C" int of_gather_gemm_tc(const of_gemm_args* args, void* stream) { return run_tc(args, 1, stream); }
+
+namespace of {
+
+// Second pass of a split-K GEMM: out[m, :] = sum over the K ranges (in range order: bit-reproducible) of the fp32 partial
+// slabs + bias + emb[sample] + residual, stored in the activation dtype, and -- like the single-pass epilogue -- the
+// group-norm partial statistics of the fp32 values before rounding.  One thread per (32-row chunk, 4 columns), rows in
+// order; a new statistics segment starts at every change of sample id (gn_stats_kernel's scheme, csrc/norm.cu).
+template <int GRAN>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(of_gemm_args g, const float* __restrict__ ws, int splits) {
+  const int tpr = g.N / 4;                                  // threads per chunk
+  const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t chunk = gidx / tpr;
+  const int cv = (int)(gidx - chunk * tpr) * 4;
+  const int64_t r0 = chunk * 32;
+  if (r0 >= g.M) return;
+  const int64_t r1 = r0 + 32 < g.M ? r0 + 32 : (int64_t)g.M;
+  float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g.bias != nullptr) badd = make_float4(g.bias[cv], g.bias[cv + 1], g.bias[cv + 2], g.bias[cv + 3]);
+  const bool st = g.stat_out != nullptr;
+  constexpr int G = 4 / GRAN;                               // granules per thread
+  float sum[G], sq[G];
+#pragma unroll
+  for (int i = 0; i < G; ++i) { sum[i] = 0.0f; sq[i] = 0.0f; }
+  int seg = st ? g.stat_chunk_seg[chunk] : 0;
+  const int half = g.N / GRAN * 2;
+  auto sample_of = [&](int64_t r) { return g.stat_sample ? g.stat_sample[r] : (int)(r / g.stat_rows_per_sample); };
+  int cur = st ? sample_of(r0) : 0;
+  auto flush = [&]() {
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      *reinterpret_cast<float2*>(g.stat_out + (int64_t)g.stat_seg_slot[seg] * half + (cv / GRAN + i) * 2) = make_float2(sum[i], sq[i]);
+      sum[i] = 0.0f; sq[i] = 0.0f;
+    }
+  };
+  const int64_t slab = (int64_t)g.M * g.N;
+  for (int64_t r = r0; r < r1; ++r) {
+    float4 v = *reinterpret_cast<const float4*>(ws + r * g.N + cv);
+    for (int sidx = 1; sidx < splits; ++sidx) {
+      const float4 t = *reinterpret_cast<const float4*>(ws + sidx * slab + r * g.N + cv);
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    v.x += badd.x; v.y += badd.y; v.z += badd.z; v.w += badd.w;
+    if (g.row_add != nullptr) {
+      const float* e = g.row_add + (int64_t)g.row_add_idx[r] * g.ld_row_add + cv;
+      v.x += e[0]; v.y += e[1]; v.z += e[2]; v.w += e[3];
+    }
+    if (g.resid != nullptr) {
+      const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(g.resid) + r * g.ld_resid + cv;
+      v.x += __bfloat162float(q[0]); v.y += __bfloat162float(q[1]); v.z += __bfloat162float(q[2]); v.w += __bfloat162float(q[3]);
+    }
+    if (g.out_f32) {
+      float* o = reinterpret_cast<float*>(g.out) + r * g.ldo + cv;
+      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + r * g.ldo + cv;
+      o[0] = __float2bfloat16_rn(v.x); o[1] = __float2bfloat16_rn(v.y); o[2] = __float2bfloat16_rn(v.z); o[3] = __float2bfloat16_rn(v.w);
+    }
+    if (st) {
+      const int b = sample_of(r);
+      if (b != cur) { flush(); ++seg; cur = b; }
+      const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { sum[i / GRAN] += f[i]; sq[i / GRAN] = fmaf(f[i], f[i], sq[i / GRAN]); }
+    }
+  }
+  if (st) flush();
+}
+
+// How many K ranges of_gather_gemm_tc_splitk should use for this launch (1 = do not split): only for launches whose
+// 128-row tiles cannot fill half of the SMs, whole K blocks per range, at least 4 per range, at most one wave of CTAs.
+static int splitk_plan(const of_gemm_args& a) {
+  if (a.dtype != OF_BF16 || a.c0 % 64 != 0 || a.c1 % 64 != 0 || a.N % 32 != 0 || a.out_rows != nullptr || a.M <= 0 ||
+      a.a_silu || (a.ntype > 0 && a.nt_block == nullptr))
+    return 1;
+  if (g_cg < 0) g_cg = env_int("OCTFUSION_TC_CG", 1);
+  if (g_tg < 0) g_tg = env_int("OCTFUSION_TC_TMAG", 0);
+  static int off = -1;
+  if (off < 0) off = env_int("OCTFUSION_TC_SPLITK", 1) ? 0 : 1;
+  if (off || g_cg == 2 || g_tg == 1) return 1;
+  const int num_kb = (a.c0 + a.c1) / 64 * a.taps + (a.ntype > 0 ? 1 : 0);
+  const int bn = a.N % 256 == 0 ? 256 : a.N % 128 == 0 ? 128 : a.N % 64 == 0 ? 64 : 32;
+  const int64_t tiles = (int64_t)((a.M + 127) / 128) * (a.N / bn);
+  const int sms = num_sms();
+  if (tiles * 2 > sms) return 1;
+  int best = 1;
+  for (int d = 2; d <= num_kb / 4 && tiles * d <= sms; ++d)
+    if (num_kb % d == 0) best = d;
+  return best;
+}
+
+}  // namespace of
+
+extern "C" int of_tc_splitk_plan(const of_gemm_args* args) {
+  if (args == nullptr) return 1;
+  return of::splitk_plan(*args);
+}
+
+extern "C" int of_gather_gemm_tc_splitk(const of_gemm_args* args, int32_t splits, float* workspace, void* stream) {
+  OF_REQUIRE(args != nullptr && workspace != nullptr && splits >= 2, "of_gather_gemm_tc_splitk: bad arguments");
+  OF_REQUIRE(splits == of::splitk_plan(*args), "of_gather_gemm_tc_splitk: splits=%d is not the plan for this launch", splits);
+  const of_gemm_args& a = *args;
+  if (a.stat_out != nullptr) {
+    OF_REQUIRE(a.stat_chunk_seg != nullptr && a.stat_seg_slot != nullptr && (a.stat_sample != nullptr || a.stat_rows_per_sample > 0),
+               "of_gather_gemm_tc_splitk: stat_out needs stat_chunk_seg, stat_seg_slot and a sample map");
+  }
+  OF_REQUIRE((a.row_add == nullptr) == (a.row_add_idx == nullptr), "of_gather_gemm_tc_splitk: row_add and row_add_idx go together");
+  of_gemm_args part = a;                                   // pass 1: plain fp32 partial sums into the workspace slabs
+  part.out = workspace; part.ldo = a.N; part.out_f32 = 1;
+  part.bias = nullptr; part.row_add = nullptr; part.row_add_idx = nullptr; part.resid = nullptr; part.stat_out = nullptr;
+  int rc = run_tc(&part, splits, stream);
+  if (rc) return rc;
+  const int64_t threads = (int64_t)((a.M + 31) / 32) * (a.N / 4);
+  const int grid = (int)((threads + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a.N % 128 == 0) of::splitk_reduce_kernel<4><<<grid, 256, 0, st>>>(a, workspace, splits);
+  else of::splitk_reduce_kernel<2><<<grid, 256, 0, st>>>(a, workspace, splits);
+  OF_LAUNCH_CHECK("of_gather_gemm_tc_splitk (reduce)");
+  return OF_OK;
 }

@@ -184,6 +184,7 @@ class Stats:
 
 
 _FUSE_STATS = os.environ.get('OCTFUSION_GN_FUSE', '1') != '0'     # 0: always run the stand-alone statistics pass
+_SPLIT_K = os.environ.get('OCTFUSION_TC_SPLITK', '1') != '0'   # split-K for small-M tcgen05 GEMMs (experiments: 0 = off)
 
 
 class PreparedWeight:
@@ -324,7 +325,13 @@ def gather_gemm(a0, w: PreparedWeight, *, a1=None, tap: TapTable = None, in_rows
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     if use_tc:
-        check(lib.of_gather_gemm_tc(C.byref(g), stream()), 'of_gather_gemm_tc')
+        # launches whose row tiles cannot fill the GPU (the dense 4^3 level: 2048 rows, K up to 13824) split K over CTAs
+        splits = lib.of_tc_splitk_plan(C.byref(g)) if _SPLIT_K else 1
+        if splits > 1:
+            ws = torch.empty((splits, m, n), dtype=torch.float32, device=a0.device)
+            check(lib.of_gather_gemm_tc_splitk(C.byref(g), splits, ptr(ws), stream()), 'of_gather_gemm_tc_splitk')
+        else:
+            check(lib.of_gather_gemm_tc(C.byref(g), stream()), 'of_gather_gemm_tc')
     else:
         check(lib.of_gather_gemm_simt(C.byref(g), stream()), 'of_gather_gemm_simt')
     if prof is not None:

@@ -187,6 +187,39 @@ def test_linear_epilogues(dtype, m, k, n):
         assert relerr(y, ref) < 8e-3
 
 
+@pytest.mark.parametrize('m,k,n', [(1000, 2048, 256), (2048, 3456, 128), (300, 1536, 64), (2048, 6912, 32)])
+def test_gemm_split_k(m, k, n):
+    """small M, long K (the dense 4^3 level of the LR U-Net): of_tc_splitk_plan cuts K into ranges computed by different
+    CTAs (fp32 partial slabs), the reduce pass adds them in order with bias / emb / residual and produces the norm
+    statistics -- same result as the single-pass kernel up to fp32 summation order, and bit-reproducible"""
+    from octfusion_b200 import ops
+    from octfusion_b200._lib import lib, GemmArgs
+    from octfusion_b200.ops import PreparedWeight
+    x, w = _rand((m, k), 1), _rand((n, k), 2, 1 / math.sqrt(k))
+    bias, resid = _rand((n,), 3), _rand((m, n), 4)
+    emb = _rand((7, n), 5)
+    idx = torch.randint(0, 7, (m,), generator=torch.Generator().manual_seed(6)).int()
+    pw = PreparedWeight(1, k, 0, n).refresh(w.to(DEV), 'linear')
+    plan = ops.StatPlan(m, batch=4, rows_per_sample=(m + 3) // 4, device=DEV) if n % 32 == 0 else None
+    run = lambda: ops.gather_gemm(x.to(DEV).bfloat16(), pw, bias=bias.to(DEV), resid=resid.to(DEV).bfloat16(),  # noqa: E731
+                                  row_add=emb.to(DEV), row_add_idx=idx.to(DEV), stats=plan)
+    assert ops._SPLIT_K
+    launches0 = lib.of_launch_count()
+    y = run()
+    assert lib.of_launch_count() - launches0 == 2, 'expected the split-K pair of launches'
+    y2 = run()
+    assert torch.equal(y, y2) and torch.equal(y._of_stats.part, y2._of_stats.part)
+    ops._SPLIT_K = False
+    try:
+        y1 = run()
+    finally:
+        ops._SPLIT_K = True
+    ref = _bf(x) @ _bf(w).t() + bias + _bf(resid) + emb[idx.long()]
+    assert relerr(y.float().cpu(), ref) < 8e-3
+    assert relerr(y.float().cpu(), y1.float().cpu()) < 3e-3
+    assert relerr(y._of_stats.part.cpu(), y1._of_stats.part.cpu()) < 1e-4
+
+
 def test_gemm_row_maps_and_concat():
     from octfusion_b200 import ops
     from octfusion_b200.ops import PreparedWeight
