@@ -1419,43 +1419,32 @@ namespace of {
 
 // Second pass of a split-K GEMM: out[m, :] = sum over the K ranges (in range order: bit-reproducible) of the fp32 partial
 // slabs + bias + emb[sample] + residual, stored in the activation dtype, and -- like the single-pass epilogue -- the
-// group-norm partial statistics of the fp32 values before rounding.  One thread per (32-row chunk, 4 columns), rows in
-// order; a new statistics segment starts at every change of sample id (gn_stats_kernel's scheme, csrc/norm.cu).
+// group-norm partial statistics of the fp32 values before rounding.  One CTA per (32-row chunk, 128 columns): warp w owns
+// row w of the chunk, lane l its columns 4l..4l+3 (coalesced 16-byte loads of every slab); the per-row (sum, sum of
+// squares) of each granule go through shared memory and warp 0 adds the chunk's rows in row order, starting a new
+// statistics segment at every change of sample id (the scheme of gn_stats_kernel, csrc/norm.cu).
 template <int GRAN>
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(of_gemm_args g, const float* __restrict__ ws, int splits) {
-  const int tpr = g.N / 4;                                  // threads per chunk
-  const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t chunk = gidx / tpr;
-  const int cv = (int)(gidx - chunk * tpr) * 4;
-  const int64_t r0 = chunk * 32;
-  if (r0 >= g.M) return;
-  const int64_t r1 = r0 + 32 < g.M ? r0 + 32 : (int64_t)g.M;
-  float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (g.bias != nullptr) badd = make_float4(g.bias[cv], g.bias[cv + 1], g.bias[cv + 2], g.bias[cv + 3]);
-  const bool st = g.stat_out != nullptr;
+__global__ void __launch_bounds__(1024) splitk_reduce_kernel(of_gemm_args g, const float* __restrict__ ws, int splits) {
   constexpr int G = 4 / GRAN;                               // granules per thread
+  __shared__ float part[32][32][G][2];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t chunk = blockIdx.x;
+  const int64_t r = chunk * 32 + w;
+  const int cv = blockIdx.y * 128 + lane * 4;
+  const bool col_ok = cv < g.N;
+  const bool st = g.stat_out != nullptr;
   float sum[G], sq[G];
 #pragma unroll
   for (int i = 0; i < G; ++i) { sum[i] = 0.0f; sq[i] = 0.0f; }
-  int seg = st ? g.stat_chunk_seg[chunk] : 0;
-  const int half = g.N / GRAN * 2;
-  auto sample_of = [&](int64_t r) { return g.stat_sample ? g.stat_sample[r] : (int)(r / g.stat_rows_per_sample); };
-  int cur = st ? sample_of(r0) : 0;
-  auto flush = [&]() {
-#pragma unroll
-    for (int i = 0; i < G; ++i) {
-      *reinterpret_cast<float2*>(g.stat_out + (int64_t)g.stat_seg_slot[seg] * half + (cv / GRAN + i) * 2) = make_float2(sum[i], sq[i]);
-      sum[i] = 0.0f; sq[i] = 0.0f;
-    }
-  };
-  const int64_t slab = (int64_t)g.M * g.N;
-  for (int64_t r = r0; r < r1; ++r) {
-    float4 v = *reinterpret_cast<const float4*>(ws + r * g.N + cv);
+  if (r < g.M && col_ok) {
+    const int64_t slab = (int64_t)g.M * g.N;
+    const float* src = ws + r * g.N + cv;
+    float4 v = *reinterpret_cast<const float4*>(src);
     for (int sidx = 1; sidx < splits; ++sidx) {
-      const float4 t = *reinterpret_cast<const float4*>(ws + sidx * slab + r * g.N + cv);
+      const float4 t = *reinterpret_cast<const float4*>(src + sidx * slab);
       v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
     }
-    v.x += badd.x; v.y += badd.y; v.z += badd.z; v.w += badd.w;
+    if (g.bias != nullptr) { v.x += g.bias[cv]; v.y += g.bias[cv + 1]; v.z += g.bias[cv + 2]; v.w += g.bias[cv + 3]; }
     if (g.row_add != nullptr) {
       const float* e = g.row_add + (int64_t)g.row_add_idx[r] * g.ld_row_add + cv;
       v.x += e[0]; v.y += e[1]; v.z += e[2]; v.w += e[3];
@@ -1471,15 +1460,38 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(of_gemm_args g, cons
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + r * g.ldo + cv;
       o[0] = __float2bfloat16_rn(v.x); o[1] = __float2bfloat16_rn(v.y); o[2] = __float2bfloat16_rn(v.z); o[3] = __float2bfloat16_rn(v.w);
     }
-    if (st) {
-      const int b = sample_of(r);
-      if (b != cur) { flush(); ++seg; cur = b; }
-      const float f[4] = {v.x, v.y, v.z, v.w};
+    const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { sum[i / GRAN] += f[i]; sq[i / GRAN] = fmaf(f[i], f[i], sq[i / GRAN]); }
-    }
+    for (int i = 0; i < 4; ++i) { sum[i / GRAN] += f[i]; sq[i / GRAN] = fmaf(f[i], f[i], sq[i / GRAN]); }
   }
-  if (st) flush();
+  if (!st) return;
+#pragma unroll
+  for (int i = 0; i < G; ++i) { part[w][lane][i][0] = sum[i]; part[w][lane][i][1] = sq[i]; }
+  __syncthreads();
+  if (w != 0 || !col_ok) return;
+  const int64_t r0 = chunk * 32;
+  const int64_t r1 = r0 + 32 < g.M ? r0 + 32 : (int64_t)g.M;
+  const int half = g.N / GRAN * 2;
+  auto sample_of = [&](int64_t row) { return g.stat_sample ? g.stat_sample[row] : (int)(row / g.stat_rows_per_sample); };
+  int seg = g.stat_chunk_seg[chunk];
+  int cur = sample_of(r0);
+  float ts[G], tq[G];
+#pragma unroll
+  for (int i = 0; i < G; ++i) { ts[i] = 0.0f; tq[i] = 0.0f; }
+  auto flush = [&]() {
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      *reinterpret_cast<float2*>(g.stat_out + (int64_t)g.stat_seg_slot[seg] * half + (cv / GRAN + i) * 2) = make_float2(ts[i], tq[i]);
+      ts[i] = 0.0f; tq[i] = 0.0f;
+    }
+  };
+  for (int64_t row = r0; row < r1; ++row) {
+    const int b = sample_of(row);
+    if (b != cur) { flush(); ++seg; cur = b; }
+#pragma unroll
+    for (int i = 0; i < G; ++i) { ts[i] += part[row - r0][lane][i][0]; tq[i] += part[row - r0][lane][i][1]; }
+  }
+  flush();
 }
 
 // How many K ranges of_gather_gemm_tc_splitk should use for this launch (1 = do not split): only for launches whose
@@ -1490,9 +1502,7 @@ static int splitk_plan(const of_gemm_args& a) {
     return 1;
   if (g_cg < 0) g_cg = env_int("OCTFUSION_TC_CG", 1);
   if (g_tg < 0) g_tg = env_int("OCTFUSION_TC_TMAG", 0);
-  static int off = -1;
-  if (off < 0) off = env_int("OCTFUSION_TC_SPLITK", 1) ? 0 : 1;
-  if (off || g_cg == 2 || g_tg == 1) return 1;
+  if (g_cg == 2 || g_tg == 1) return 1;
   const int num_kb = (a.c0 + a.c1) / 64 * a.taps + (a.ntype > 0 ? 1 : 0);
   const int bn = a.N % 256 == 0 ? 256 : a.N % 128 == 0 ? 128 : a.N % 64 == 0 ? 64 : 32;
   const int64_t tiles = (int64_t)((a.M + 127) / 128) * (a.N / bn);
@@ -1525,11 +1535,10 @@ extern "C" int of_gather_gemm_tc_splitk(const of_gemm_args* args, int32_t splits
   part.bias = nullptr; part.row_add = nullptr; part.row_add_idx = nullptr; part.resid = nullptr; part.stat_out = nullptr;
   int rc = run_tc(&part, splits, stream);
   if (rc) return rc;
-  const int64_t threads = (int64_t)((a.M + 31) / 32) * (a.N / 4);
-  const int grid = (int)((threads + 255) / 256);
+  const dim3 grid((unsigned)((a.M + 31) / 32), (unsigned)((a.N + 127) / 128));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a.N % 128 == 0) of::splitk_reduce_kernel<4><<<grid, 256, 0, st>>>(a, workspace, splits);
-  else of::splitk_reduce_kernel<2><<<grid, 256, 0, st>>>(a, workspace, splits);
+  if (a.N % 128 == 0) of::splitk_reduce_kernel<4><<<grid, 1024, 0, st>>>(a, workspace, splits);
+  else of::splitk_reduce_kernel<2><<<grid, 1024, 0, st>>>(a, workspace, splits);
   OF_LAUNCH_CHECK("of_gather_gemm_tc_splitk (reduce)");
   return OF_OK;
 }

@@ -184,7 +184,10 @@ class Stats:
 
 
 _FUSE_STATS = os.environ.get('OCTFUSION_GN_FUSE', '1') != '0'     # 0: always run the stand-alone statistics pass
-_SPLIT_K = os.environ.get('OCTFUSION_TC_SPLITK', '1') != '0'   # split-K for small-M tcgen05 GEMMs (experiments: 0 = off)
+# split-K for small-M tcgen05 GEMMs (of_gather_gemm_tc_splitk): opt-in.  Measured -0.17 ms per step, but the different
+# rounding pattern moves the bf16 max-norm error of the dense LR nets by +-5 %, and those parity tests sit at their
+# tolerance (1.94e-2 of 2e-2): the default keeps the single-pass kernel with the small-M tile dispatch.
+_SPLIT_K = os.environ.get('OCTFUSION_TC_SPLITK', '0') == '1'
 
 
 class PreparedWeight:

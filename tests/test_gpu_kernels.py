@@ -203,20 +203,22 @@ def test_gemm_split_k(m, k, n):
     plan = ops.StatPlan(m, batch=4, rows_per_sample=(m + 3) // 4, device=DEV) if n % 32 == 0 else None
     run = lambda: ops.gather_gemm(x.to(DEV).bfloat16(), pw, bias=bias.to(DEV), resid=resid.to(DEV).bfloat16(),  # noqa: E731
                                   row_add=emb.to(DEV), row_add_idx=idx.to(DEV), stats=plan)
-    assert ops._SPLIT_K
-    launches0 = lib.of_launch_count()
-    y = run()
-    assert lib.of_launch_count() - launches0 == 2, 'expected the split-K pair of launches'
-    y2 = run()
-    assert torch.equal(y, y2) and torch.equal(y._of_stats.part, y2._of_stats.part)
-    ops._SPLIT_K = False
+    keep = ops._SPLIT_K
+    y1 = None
     try:
-        y1 = run()
-    finally:
+        ops._SPLIT_K = False
+        y1 = run()                                           # single pass (also packs the weight image)
         ops._SPLIT_K = True
+        launches0 = lib.of_launch_count()
+        y = run()
+        assert lib.of_launch_count() - launches0 == 2, 'expected the split-K pair of launches'
+        y2 = run()
+    finally:
+        ops._SPLIT_K = keep
+    assert torch.equal(y, y2) and torch.equal(y._of_stats.part, y2._of_stats.part)
     ref = _bf(x) @ _bf(w).t() + bias + _bf(resid) + emb[idx.long()]
     assert relerr(y.float().cpu(), ref) < 8e-3
-    assert relerr(y.float().cpu(), y1.float().cpu()) < 3e-3
+    assert relerr(y.float().cpu(), y1.float().cpu()) < 8e-3          # (max norm: one bf16 ulp at the top of the range)
     assert relerr(y._of_stats.part.cpu(), y1._of_stats.part.cpu()) < 1e-4
 
 
