@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     int it = 0, tn = 0;
     for (int tile = w_first; tile < total_tiles; tile += w_stride, ++it) {
       const int vtile = g.reverse ? total_tiles - 1 - tile : tile;
-      const int ptile = vtile / p.ksplit;
+      const int ptile = p.ksplit == 1 ? vtile : vtile / p.ksplit;
       const int64_t split_row0 = (int64_t)(vtile - ptile * p.ksplit) * g.M;        // this K range's slab of the workspace
       const int mt0 = (ptile / p.n_tiles) * TILE_ROWS + (int)rank * TC_BM, n0 = (ptile % p.n_tiles) * BN;
       const int as = it & 1;
@@ -842,8 +842,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     for (int tile = w_first; tile < total_tiles; tile += w_stride) {
       // a CTA of a pair streams its half of the tile's weight rows
       const int vtile = g.reverse ? total_tiles - 1 - tile : tile;
-      const int n0 = ((vtile / p.ksplit) % p.n_tiles) * BN + (int)rank * (BN / CG);
-      const int kb_off = (vtile % p.ksplit) * p.num_kb;            // first K block of this virtual tile's range
+      const int otile = p.ksplit == 1 ? vtile : vtile / p.ksplit;
+      const int n0 = (otile % p.n_tiles) * BN + (int)rank * (BN / CG);
+      const int kb_off = (vtile - otile * p.ksplit) * p.num_kb;    // first K block of this virtual tile's range
       for (int kb = 0; kb < p.num_kb; kb += KSUB) {
         const uint32_t bfull = U1 ? bar_full + 8 * stage : bar_bfull + 8 * stage;
         mbar_wait((U1 ? bar_empty : bar_bempty) + 8 * stage, phase ^ 1);
@@ -883,13 +884,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
       const uint32_t slot_total = (uint32_t)my_tiles * slots;
       struct Pos { int ti, s, kb, cb, tap; };
       auto vtile_of = [&](int ti) { const int tile = w_first + ti * w_stride; return g.reverse ? total_tiles - 1 - tile : tile; };
-      auto kb_off = [&](int ti) { return (vtile_of(ti) % p.ksplit) * p.num_kb; };
+      auto kb_off = [&](int ti) { return p.ksplit == 1 ? 0 : (vtile_of(ti) % p.ksplit) * p.num_kb; };
       auto norm = [&](Pos& c) {
         while (c.s >= (int)slots) { c.s -= (int)slots; ++c.ti; c.kb = c.s / MT; c.cb = 0; c.tap = kb_off(c.ti) + c.kb; }
         while (c.tap >= taps) { c.tap -= taps; ++c.cb; }
       };
       auto tile_m0 = [&](int ti) {
-        const int ptile = vtile_of(ti) / p.ksplit;
+        const int ptile = p.ksplit == 1 ? vtile_of(ti) : vtile_of(ti) / p.ksplit;   // (no division on the common path)
         return (p.n_tiles == 1 ? ptile : ptile / p.n_tiles) * TILE_ROWS + (h + (int)rank) * TC_BM;
       };
       auto fetch_taps = [&](const Pos& c, int32_t* t) {
@@ -982,14 +983,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     // incrementally -- no integer divisions in the producer loop (its instruction stream competes with the MMA warp)
     struct Pos { int ti, s, kb, cb, tap; };
     auto vtile_of = [&](int ti) { const int tile = w_first + ti * w_stride; return g.reverse ? total_tiles - 1 - tile : tile; };
-    auto kb_off = [&](int ti) { return (vtile_of(ti) % p.ksplit) * p.num_kb; };
+    auto kb_off = [&](int ti) { return p.ksplit == 1 ? 0 : (vtile_of(ti) % p.ksplit) * p.num_kb; };
     auto norm = [&](Pos& c) {
       // (cb, tap) = the ABSOLUTE K block kb_off + kb of the tile's K range (split-K), kb stays relative to the range
       while (c.s >= (int)slots) { c.s -= (int)slots; ++c.ti; c.kb = c.s / MT; c.cb = 0; c.tap = kb_off(c.ti) + c.kb; }
       while (c.tap >= taps) { c.tap -= taps; ++c.cb; }
     };
     auto tile_m0 = [&](int ti) {
-      const int ptile = vtile_of(ti) / p.ksplit;
+      const int ptile = p.ksplit == 1 ? vtile_of(ti) : vtile_of(ti) / p.ksplit;   // (no division on the common path)
       return (p.n_tiles == 1 ? ptile : ptile / p.n_tiles) * TILE_ROWS + (h + (int)rank) * TC_BM;
     };
     auto fetch_taps = [&](const Pos& c, int32_t* t) {
