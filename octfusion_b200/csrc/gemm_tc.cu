@@ -433,8 +433,12 @@ __device__ __forceinline__ void warp_reduce_vals(float (&a)[NV], int lane) {
 // ------------------------------------------------------------------------------------------------
 // TG = 1: the gathered tiles are filled by the TMA (tile::gather4, one instruction per 4 rows, one warp per 16 KB
 // sub-tile) instead of 16-byte cp.async copies of 8 producer warps.
-template <int BN, int MT, int UNI, int CG, int TG>
+// SK = 1: split-K instantiation (TcParams::ksplit K ranges per output tile).  A template parameter, not a run-time test: the
+// tile-index arithmetic and the extra live values of the split path cost registers in the epilogue (measured: +10 % on the
+// epilogue-bound layers when every launch carried them), so the common SK = 0 kernels are compiled without.
+template <int BN, int MT, int UNI, int CG, int TG, int SK>
 __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  const int ksplit = SK ? p.ksplit : 1;                    // (compile-time 1 for SK = 0: the divisions below fold away)
   using Cfg = TcCfg<BN, MT, UNI, CG>;
   constexpr bool U1 = Cfg::UNIFIED;                        // weight tile inside the gather ring's stage
   constexpr int KSUB = Cfg::KSUB, SUBS = Cfg::SUBS;
@@ -460,7 +464,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
   const of_gemm_args& g = p.g;
   const int taps = g.taps;
   // work items: CTA tiles of 128*MT rows (CG = 1) or pair tiles of 256 rows that both CTAs of a pair walk together
-  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;   // virtual tile v: output tile v / ksplit, K range v % ksplit
+  const int total_tiles = p.m_tiles * p.n_tiles * ksplit;   // virtual tile v: output tile v / ksplit, K range v % ksplit
   uint32_t rank = 0;
   if constexpr (CG == 2) rank = cluster_ctarank();
   const int w_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -508,8 +512,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     int it = 0, tn = 0;
     for (int tile = w_first; tile < total_tiles; tile += w_stride, ++it) {
       const int vtile = g.reverse ? total_tiles - 1 - tile : tile;
-      const int ptile = p.ksplit == 1 ? vtile : vtile / p.ksplit;
-      const int64_t split_row0 = (int64_t)(vtile - ptile * p.ksplit) * g.M;        // this K range's slab of the workspace
+      const int ptile = vtile / ksplit;
+      const int64_t split_row0 = (int64_t)(vtile - ptile * ksplit) * g.M;        // this K range's slab of the workspace
       const int mt0 = (ptile / p.n_tiles) * TILE_ROWS + (int)rank * TC_BM, n0 = (ptile % p.n_tiles) * BN;
       const int as = it & 1;
       mbar_wait_relaxed(bar_tfull + 8 * as, (it >> 1) & 1);
@@ -842,9 +846,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     for (int tile = w_first; tile < total_tiles; tile += w_stride) {
       // a CTA of a pair streams its half of the tile's weight rows
       const int vtile = g.reverse ? total_tiles - 1 - tile : tile;
-      const int otile = p.ksplit == 1 ? vtile : vtile / p.ksplit;
+      const int otile = vtile / ksplit;
       const int n0 = (otile % p.n_tiles) * BN + (int)rank * (BN / CG);
-      const int kb_off = (vtile - otile * p.ksplit) * p.num_kb;    // first K block of this virtual tile's range
+      const int kb_off = (vtile - otile * ksplit) * p.num_kb;    // first K block of this virtual tile's range
       for (int kb = 0; kb < p.num_kb; kb += KSUB) {
         const uint32_t bfull = U1 ? bar_full + 8 * stage : bar_bfull + 8 * stage;
         mbar_wait((U1 ? bar_empty : bar_bempty) + 8 * stage, phase ^ 1);
@@ -884,13 +888,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
       const uint32_t slot_total = (uint32_t)my_tiles * slots;
       struct Pos { int ti, s, kb, cb, tap; };
       auto vtile_of = [&](int ti) { const int tile = w_first + ti * w_stride; return g.reverse ? total_tiles - 1 - tile : tile; };
-      auto kb_off = [&](int ti) { return p.ksplit == 1 ? 0 : (vtile_of(ti) % p.ksplit) * p.num_kb; };
+      auto kb_off = [&](int ti) { return (vtile_of(ti) % ksplit) * p.num_kb; };
       auto norm = [&](Pos& c) {
         while (c.s >= (int)slots) { c.s -= (int)slots; ++c.ti; c.kb = c.s / MT; c.cb = 0; c.tap = kb_off(c.ti) + c.kb; }
         while (c.tap >= taps) { c.tap -= taps; ++c.cb; }
       };
       auto tile_m0 = [&](int ti) {
-        const int ptile = p.ksplit == 1 ? vtile_of(ti) : vtile_of(ti) / p.ksplit;   // (no division on the common path)
+        const int ptile = vtile_of(ti) / ksplit;
         return (p.n_tiles == 1 ? ptile : ptile / p.n_tiles) * TILE_ROWS + (h + (int)rank) * TC_BM;
       };
       auto fetch_taps = [&](const Pos& c, int32_t* t) {
@@ -983,14 +987,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
     // incrementally -- no integer divisions in the producer loop (its instruction stream competes with the MMA warp)
     struct Pos { int ti, s, kb, cb, tap; };
     auto vtile_of = [&](int ti) { const int tile = w_first + ti * w_stride; return g.reverse ? total_tiles - 1 - tile : tile; };
-    auto kb_off = [&](int ti) { return p.ksplit == 1 ? 0 : (vtile_of(ti) % p.ksplit) * p.num_kb; };
+    auto kb_off = [&](int ti) { return (vtile_of(ti) % ksplit) * p.num_kb; };
     auto norm = [&](Pos& c) {
       // (cb, tap) = the ABSOLUTE K block kb_off + kb of the tile's K range (split-K), kb stays relative to the range
       while (c.s >= (int)slots) { c.s -= (int)slots; ++c.ti; c.kb = c.s / MT; c.cb = 0; c.tap = kb_off(c.ti) + c.kb; }
       while (c.tap >= taps) { c.tap -= taps; ++c.cb; }
     };
     auto tile_m0 = [&](int ti) {
-      const int ptile = p.ksplit == 1 ? vtile_of(ti) : vtile_of(ti) / p.ksplit;   // (no division on the common path)
+      const int ptile = vtile_of(ti) / ksplit;
       return (p.n_tiles == 1 ? ptile : ptile / p.n_tiles) * TILE_ROWS + (h + (int)rank) * TC_BM;
     };
     auto fetch_taps = [&](const Pos& c, int32_t* t) {
@@ -1189,7 +1193,7 @@ static int make_row_map(CUtensorMap* m, const void* base, int64_t cols, int64_t 
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cap = 0, g_trace_block = 0;
 
-template <int BN, int MT, int UNI, int CG = 1, int TG = 0>
+template <int BN, int MT, int UNI, int CG = 1, int TG = 0, int SK = 0>
 static int launch_tc(TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, MT, UNI, CG>;
   // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute of the function
@@ -1197,7 +1201,7 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc_kernel<BN, MT, UNI, CG, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc_kernel<BN, MT, UNI, CG, TG, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("of_gather_gemm_tc: cudaFuncSetAttribute(%d B): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -1226,13 +1230,13 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gather_gemm_tc_kernel<BN, MT, UNI, CG, TG>, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gather_gemm_tc_kernel<BN, MT, UNI, CG, TG, SK>, p);
     if (e != cudaSuccess) {
       set_error("of_gather_gemm_tc (pair): launch: %s", cudaGetErrorString(e));
       return OF_E_CUDA;
     }
   } else {
-    gather_gemm_tc_kernel<BN, MT, UNI, CG, TG><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    gather_gemm_tc_kernel<BN, MT, UNI, CG, TG, SK><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
   }
   OF_LAUNCH_CHECK("of_gather_gemm_tc");
   return OF_OK;
@@ -1348,10 +1352,10 @@ static int run_tc(const of_gemm_args* args, int ksplit, void* stream) {
     p.ksplit = ksplit;
     p.num_kb /= ksplit;
     // one 128-row tile per CTA: the point is many short K loops
-    if (p.npad % 256 == 0) return uni == 1 ? launch_tc<256, 1, 1>(p, st) : launch_tc<256, 1, 0>(p, st);
-    if (p.npad % 128 == 0) return launch_tc<128, 1, 0>(p, st);
-    if (p.npad % 64 == 0) return launch_tc<64, 1, 0>(p, st);
-    return launch_tc<32, 1, 0>(p, st);
+    if (p.npad % 256 == 0) return launch_tc<256, 1, 1, 1, 0, 1>(p, st);
+    if (p.npad % 128 == 0) return launch_tc<128, 1, 0, 1, 0, 1>(p, st);
+    if (p.npad % 64 == 0) return launch_tc<64, 1, 0, 1, 0, 1>(p, st);
+    return launch_tc<32, 1, 0, 1, 0, 1>(p, st);
   }
   if (g_tg < 0) g_tg = env_int("OCTFUSION_TC_TMAG", 0);
   if (g_tg == 1 && a.lda0 % 64 == 0 && (a.c1 == 0 || a.lda1 % 64 == 0) && reinterpret_cast<uintptr_t>(a.a0) % 128 == 0 &&
