@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-timeout 3300 tools/final_gpu_r02.sh > gpurun_out/final_r02d.log 2>&1
-tail -n 200 gpurun_out/final_r02d.log
+timeout 3300 tools/final_gpu_r02.sh > gpurun_out/final_r02e.log 2>&1
+tail -n 200 gpurun_out/final_r02e.log
