@@ -686,7 +686,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gather_gemm_tc_kernel(const __g
                 }
               }
              };
-             if (g.N % 128 == 0) stats(std::integral_constant<int, 4>{});
+             // (a tile of >= 128 columns divides N: the granule is known at compile time there -- compiling both paths into
+             // the wide kernels cost them registers in this loop, +8 % on the 128-wide layers)
+             if constexpr (BN >= 128) stats(std::integral_constant<int, 4>{});
+             else if (g.N % 128 == 0) stats(std::integral_constant<int, 4>{});
              else stats(std::integral_constant<int, 2>{});
             }
           }
