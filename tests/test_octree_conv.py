@@ -35,7 +35,7 @@ def test_oracle_octree_conv_is_conv3d_on_a_full_layer():
 
 
 def test_oracle_neighbours_are_symmetric_on_adaptive_layers():
-    dg, _ = oracle_doctree(2, 0)
+    dg, _ = oracle_doctree(1, 0)                                                   # (the restatement is a Python loop per node)
     for d in (5, 6):
         nb = R.octree_neigh27(dg.octree, d)
         n = nb.shape[0]
