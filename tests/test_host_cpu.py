@@ -38,6 +38,28 @@ def test_argument_validation_without_gpu():
     assert _lib.lib.of_pack_weight_tc_bytes(7, 128, 5, 128) == (7 * 2 + 1) * 128 * 64 * 2
 
 
+def test_splitk_plan_host_logic():
+    """of_tc_splitk_plan is pure host arithmetic (148 SMs assumed without a device): split only launches whose 128-row
+    tiles cannot fill half of the SMs, into whole K blocks, at least 4 per range, at most one wave of CTAs"""
+    from octfusion_b200 import _lib
+    def plan(m, n, c, taps, ntype=0, out_rows=None):
+        g = _lib.GemmArgs()
+        g.M, g.N, g.c0, g.c1, g.taps, g.ntype, g.dtype = m, n, c, 0, taps, ntype, 1          # dtype 1 = bf16
+        g.out_rows = out_rows
+        return _lib.lib.of_tc_splitk_plan(ctypes.byref(g))
+    if torch.cuda.is_available() and torch.cuda.get_device_properties(0).multi_processor_count != 148:
+        pytest.skip('the expected plans below are for 148 SMs')
+    assert plan(2048, 256, 256, 27) == 9          # 108 K blocks, 16 tiles: 9 ranges of 12 (144 CTAs)
+    assert plan(2048, 128, 512, 27) == 9          # 216 K blocks, 16 tiles
+    assert plan(2048, 128, 128, 27) == 9          # 54 K blocks: 9 ranges of 6
+    assert plan(2048, 256, 256, 1) == 1           # 4 K blocks: nothing to split
+    assert plan(16384, 128, 128, 27) == 1         # 128 tiles already fill the SMs
+    assert plan(907484, 128, 128, 7, 5) == 1
+    assert plan(2048, 250, 256, 27) == 1          # N must be a multiple of 32
+    assert plan(2048, 256, 100, 27) == 1          # c must be a multiple of 64 (tcgen05 path)
+    assert _lib.lib.of_tc_splitk_plan(None) == 1
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip('only meaningful on a host without a GPU')
